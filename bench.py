@@ -1,0 +1,461 @@
+#!/usr/bin/env python3
+"""Throughput benchmark of the Lucas-Kanade hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload single_1080p|pyramidal_4k]
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic frame pairs per GPU.
+Default workload (BASELINE.json configs[2]): single-scale LK, 256 x 1920x1080 float32 frame
+pairs per GPU, 5x5 window, fast mode.  Frame pairs are independent, so N GPUs each take
+their own batch with no data-path collective ("scaling": "weak").
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events on the
+launch stream, max over ranks); `e2e` goes through the host-buffer C-ABI entry point with
+pinned host arrays, H2D and D2H inside the timed region; `roofline` is the fused kernel's
+algorithmic bytes (16 B/pixel) over its measured duration against the measured HBM peak;
+`cpu_baseline` is the CPU oracle (vectorised NumPy port of the reference) on a bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+BACKEND = ROOT / "optical-flow-fpga_b200"
+for _p in (str(ROOT), str(BACKEND)):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (batch per GPU, H, W, pyramidal?, levels, iterations)
+    "single_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1),
+    "pyramidal_4k": dict(batch=16, H=2160, W=3840, pyramidal=True, levels=3, iters=3),
+}
+WINDOW = 5
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.load(open(f))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def pyramidal_bytes_per_pixel(levels: int, iters: int) -> float:
+    """Stage-fused traffic model of SURVEY.md 8(d): pyramid 2 frames x (N_{l-1}+N_l) x 4 B,
+    24 B per executed iteration and level pixel, 8 B per upsampled pixel."""
+    n = [1.0 / 4**l for l in range(levels)]
+    b = sum(2 * (n[l - 1] + n[l]) * 4 for l in range(1, levels))
+    b += sum(24 * iters * n[l] for l in range(levels))
+    b += sum(8 * n[l] for l in range(levels - 1))
+    return b
+
+
+# ---------------------------------------------------------------------------------------
+# clocks during the timed region (NVML, sampled from a thread)
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+        self.period = period_s
+
+    def _names(self, mask: int):
+        nv = self.nv
+        table = {
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        return {k for k, bit in table.items() if mask & bit}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.reasons |= self._names(int(get(self.h)))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ---------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and the --impl reference arm)
+# ---------------------------------------------------------------------------------------
+def _oracle_job(args):
+    kind, seed, rows, H, W, levels, iters = args
+    import synthetic
+    from oracle import lk_float_oracle as orc
+
+    prev, curr, _ = synthetic.make_pairs_numpy(1, rows, W, seed=seed)
+    t0 = time.perf_counter()
+    if kind == "pyramidal":
+        orc.lucas_kanade_pyramidal(prev[0], curr[0], levels, WINDOW, iters)
+    else:
+        orc.lucas_kanade_single_scale(prev[0], curr[0], WINDOW)
+    return time.perf_counter() - t0, rows * W
+
+
+def time_reference_loop_per_pixel() -> float:
+    """Microseconds per pixel of the reference-shaped scalar loop (one small crop)."""
+    from oracle import lk_float_oracle as orc
+
+    rng = np.random.default_rng(0)
+    g = [rng.standard_normal((40, 40)).astype(np.float32) for _ in range(3)]
+    t0 = time.perf_counter()
+    orc.lucas_kanade_from_gradients_loop(g[0], g[1], g[2], WINDOW)
+    return (time.perf_counter() - t0) / (36 * 36) * 1e6
+
+
+def run_oracle_sample(pool, cores: int, wl: dict, rows: int, jobs: int, seed0: int):
+    """`jobs` (= `cores`) frame-pair bands of `rows` rows each, one per worker process, all
+    running at the same time.  Frame synthesis is not timed: the step's time is the slowest
+    worker's oracle time.  Returns (Mpixel/s, pixels, seconds)."""
+    kind = "pyramidal" if wl["pyramidal"] else "single"
+    work = [(kind, seed0 + j, rows, wl["H"], wl["W"], wl["levels"], wl["iters"]) for j in range(jobs)]
+    res = pool.map(_oracle_job, work, chunksize=1)
+    pixels = sum(r[1] for r in res)
+    secs = max(r[0] for r in res)
+    return pixels / secs / 1e6, pixels, secs
+
+
+def host_cores() -> int:
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def reference_arm(args, wl, rank: int, world: int):
+    """--impl reference: the CPU port of the reference path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = host_cores()
+    steps, warmup = args.steps, args.warmup
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        # calibrate on a 64-row band, then size the per-step sample for ~120 s in total
+        t0 = time.perf_counter()
+        run_oracle_sample(pool, cores, wl, 64 if not wl["pyramidal"] else 128, cores, 1000)
+        calib = time.perf_counter() - t0
+        calib_rows = 64 if not wl["pyramidal"] else 128
+        budget = 120.0 / max(1, steps + warmup)
+        rows = int(calib_rows * budget / max(calib, 1e-3))
+        rows = max(32, min(wl["H"], rows))
+        rows -= rows % 8
+        for _ in range(warmup):
+            run_oracle_sample(pool, cores, wl, rows, cores, 2000)
+        pixels, wall = 0, 0.0
+        for s in range(steps):
+            _, px, secs = run_oracle_sample(pool, cores, wl, rows, cores, 3000 + 100 * s)
+            pixels += px
+            wall += secs
+    value = pixels / wall / 1e6
+    loop_us = time_reference_loop_per_pixel()
+    sample = f"per step: {cores} bands of {rows}x{wl['W']} px, one per worker process"
+    line = {
+        "impl": "reference",
+        "metric": "Mpixel/s",
+        "value": value,
+        "unit": "Mpixel/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": warmup,
+        "ms_per_step": wall / max(1, steps) * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args.workload, wl),
+        "cpu_baseline": {
+            "value": value,
+            "unit": "Mpixel/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": sample,
+            "note": "vectorised NumPy port of the reference (bit-exact with it); the reference's own "
+            f"per-pixel Python loop costs {loop_us:.1f} us/pixel/core here",
+        },
+        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name: str, wl: dict) -> dict:
+    if wl["pyramidal"]:
+        desc = (f"{wl['levels']}-level pyramidal LK, {wl['iters']} iterations/level, batch of {wl['batch']} synthetic "
+                f"{wl['W']}x{wl['H']} float32 frame pairs per GPU, 5x5 window")
+    else:
+        desc = f"single-scale LK, batch of {wl['batch']} synthetic {wl['W']}x{wl['H']} float32 frame pairs per GPU, 5x5 window"
+    return {
+        "workload": desc,
+        "name": name,
+        "batch_per_gpu": wl["batch"],
+        "height": wl["H"],
+        "width": wl["W"],
+        "window": WINDOW,
+        "l2": "per-step inputs + outputs are far larger than the 126 MB L2, so no flush between iterations",
+        "parallelism": "independent frame pairs sharded by rank, no data-path collective",
+    }
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+
+    import of_b200
+    import synthetic
+
+    if not torch.cuda.is_available() or of_b200.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    of_b200.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, H, W = wl["batch"], wl["H"], wl["W"]
+    pixels_per_step = B * H * W
+    prev, curr, _ = synthetic.make_pairs_torch(B, H, W, dev, seed=1234 + rank)
+    u = torch.empty_like(prev)
+    v = torch.empty_like(prev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    if wl["pyramidal"]:
+        ws_bytes = of_b200.lk_pyramidal_workspace_bytes(B, H, W, wl["levels"], wl["iters"])
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+        def step():
+            of_b200.lk_pyramidal_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
+                                     wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST, ws.data_ptr(), ws_bytes,
+                                     None, None, stream)
+    else:
+        def step():
+            of_b200.lk_single_scale_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
+                                        WINDOW, of_b200.MODE_FAST, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = of_b200.kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sampler.start()
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    sampler.stop()
+    launches = of_b200.kernel_launches() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * pixels_per_step / (ms_per_step * 1e-3) / 1e6  # Mpixel/s, whole job
+
+    # ---- parity of what was just timed (device result vs oracle on sampled pairs) ----------
+    parity = None
+    cpu_baseline = None
+    if rank == 0:
+        from oracle import lk_float_oracle as orc
+
+        idx = [0, B // 2, B - 1] if not wl["pyramidal"] else [0]
+        ok = True
+        for b in idx:
+            p_h, c_h = prev[b].cpu().numpy(), curr[b].cpu().numpy()
+            if wl["pyramidal"]:
+                uo, vo = orc.lucas_kanade_pyramidal(p_h, c_h, wl["levels"], WINDOW, wl["iters"])
+            else:
+                uo, vo = orc.lucas_kanade_single_scale(p_h, c_h, WINDOW)
+            ok &= bool(np.array_equal(u[b].cpu().numpy().view(np.uint32), uo.view(np.uint32)))
+            ok &= bool(np.array_equal(v[b].cpu().numpy().view(np.uint32), vo.view(np.uint32)))
+        parity = {"bit_exact_vs_oracle": ok, "pairs_checked": len(idx)}
+
+    # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
+    e2e = None
+    if not wl["pyramidal"]:
+        hp = of_b200.PinnedArray((B, H, W))
+        hc = of_b200.PinnedArray((B, H, W))
+        hu = of_b200.PinnedArray((B, H, W))
+        hv = of_b200.PinnedArray((B, H, W))
+        hp.array[...] = prev.cpu().numpy()
+        hc.array[...] = curr.cpu().numpy()
+        e2e_steps = max(1, min(args.steps, 5))
+        of_b200.lk_single_scale_batch(hp.array, hc.array, WINDOW, of_b200.MODE_FAST, out=(hu.array, hv.array))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            of_b200.lk_single_scale_batch(hp.array, hc.array, WINDOW, of_b200.MODE_FAST, out=(hu.array, hv.array))
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item())
+        same = bool(np.array_equal(hu.array[B - 1].view(np.uint32), u[B - 1].cpu().numpy().view(np.uint32)))
+        e2e = {
+            "value": world * pixels_per_step / (e2e_ms * 1e-3) / 1e6,
+            "unit": "Mpixel/s",
+            "h2d_bytes_per_step": 2 * pixels_per_step * 4,
+            "d2h_bytes_per_step": 2 * pixels_per_step * 4,
+            "ms_per_step": e2e_ms,
+            "steps": e2e_steps,
+            "api": "of_lk_single_scale_f32 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams",
+            "matches_device_run": same,
+        }
+        for a in (hp, hc, hu, hv):
+            a.free()
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+
+        cores = host_cores()
+        with mp.get_context("spawn").Pool(cores) as pool:
+            rows = H if not wl["pyramidal"] else 540
+            run_oracle_sample(pool, cores, wl, 64, cores, 10)  # start the workers
+            mpix, px, wall = run_oracle_sample(pool, cores, wl, rows, cores, 100)
+        cpu_baseline = {
+            "value": mpix,
+            "unit": "Mpixel/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{cores} frame-pair bands of {rows}x{W} px, one per worker process, {wall:.1f} s",
+            "reference_loop_us_per_pixel_per_core": time_reference_loop_per_pixel(),
+        }
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peak, peak_src = hbm_peak()
+    bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else 16.0
+    kernel_ms = statistics.mean(per_step)
+    achieved = bpp * pixels_per_step / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": "Mpixel/s",
+        "value": value,
+        "unit": "Mpixel/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args.workload, wl),
+        "frame_pairs_per_s": world * B / (ms_per_step * 1e-3),
+        "roofline": {
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_pixel": bpp,
+            "kernel": "lk_march_kernel<true> (one launch per step)" if not wl["pyramidal"] else "whole pyramidal step (all launches)",
+            "kernel_ms": kernel_ms,
+            "frac_of_nominal_8TBs": achieved / 8000.0,
+        },
+        "e2e": e2e,
+        "cpu_baseline": cpu_baseline,
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="single_1080p")
+    ap.add_argument("--batch", type=int, default=None, help="override frame pairs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, wl, rank, world)
+        return
+    gpu_arm(args, wl, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

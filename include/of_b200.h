@@ -1,0 +1,131 @@
+/*
+ * of_b200.h -- C ABI of libof_b200.so, the B200 (sm_100a) backend for the Lucas-Kanade
+ * hot path of rothej/optical-flow-fpga.
+ *
+ * The reference has no FFI: its hot path is a set of module-level Python functions
+ * (python/lucas_kanade_core.py, python/lucas_kanade_pyramidal.py).  Each entry point
+ * below replaces one of them and is what a ctypes binding of that function calls; the
+ * drop-in Python modules in optical-flow-fpga_b200/ are exactly such bindings.
+ * See INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - images are C-contiguous row-major [batch][height][width]; x is the column;
+ *   - every function returns OF_OK (0) or an of_status error code, never throws;
+ *     of_last_error() gives the message of the calling thread's last failure;
+ *   - the caller owns every buffer; inputs are never written;
+ *   - "host" entry points take host pointers and do H2D, kernels, D2H themselves;
+ *     "_dev" entry points take device pointers and a cudaStream_t (as void*) and only
+ *     enqueue work -- they do not synchronise;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     OF_ERR_NO_DEVICE.
+ */
+#ifndef OF_B200_H
+#define OF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum of_status {
+    OF_OK = 0,
+    OF_ERR_INVALID_ARGUMENT = 1,
+    OF_ERR_CUDA = 2,
+    OF_ERR_UNSUPPORTED = 3,
+    OF_ERR_NO_DEVICE = 4,
+    OF_ERR_OUT_OF_MEMORY = 5
+} of_status;
+
+/* Arithmetic mode of the float path.
+ * OF_MODE_EXACT  the reference's operation order (NumPy pairwise window sums, SciPy's
+ *                float64 filters): bit-identical to the Python reference on any input.
+ * OF_MODE_FAST   separable window sums in registers (the throughput kernels); bit-identical
+ *                to the reference on uint8-valued frames (all partial sums exactly
+ *                representable), tolerance-level otherwise. */
+#define OF_MODE_EXACT 0
+#define OF_MODE_FAST 1
+
+/* flags of the fixed-point mode */
+#define OF_FX_MIRROR_AVG_QUIRK 1 /* 9-bit signed average of gradient_compute.sv:116 */
+
+#define OF_MAX_WINDOW 11
+#define OF_MAX_GAUSS_RADIUS 16
+
+/* ---- library / device ---------------------------------------------------------------- */
+int of_version(void);
+const char* of_last_error(void);
+int of_device_count(void);              /* >= 0; 0 when no CUDA device is usable        */
+int of_set_device(int ordinal);
+long long of_kernel_launches(void);     /* kernels launched by this library so far      */
+int of_host_alloc_pinned(void** ptr, size_t bytes);
+int of_host_free_pinned(void* ptr);
+
+/* ---- host-buffer entry points ------------------------------------------------------- */
+
+/* compute_gradients(frame_prev, frame_curr) -> (Ix, Iy, It)
+ * replaces python/lucas_kanade_core.py:15-45 */
+int of_gradients_f32(const float* prev, const float* curr, float* ix, float* iy, float* it,
+                     int height, int width);
+
+/* lucas_kanade_from_gradients(Ix, Iy, It, window_size) -> (u, v)
+ * replaces python/lucas_kanade_core.py:73-135 */
+int of_lk_from_gradients_f32(const float* ix, const float* iy, const float* it, float* u, float* v,
+                             int height, int width, int window);
+
+/* lucas_kanade_single_scale(frame_prev, frame_curr, window_size) -> (u, v), for a batch of
+ * independent frame pairs.  replaces python/lucas_kanade_core.py:48-70 */
+int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float* v, int batch,
+                           int height, int width, int window, int mode);
+
+/* One coarser level of build_gaussian_pyramid: gaussian_filter (taps `weights`, 2*radius+1
+ * float64 values as scipy.ndimage builds them) then bilinear resampling on the
+ * np.linspace(0, n-1, out_n) grid.  replaces python/lucas_kanade_pyramidal.py:44-59 */
+int of_pyramid_down_f32(const float* src, float* dst, int height, int width, int out_height,
+                        int out_width, const double* weights, int radius);
+
+/* warp_image(image, flow_u, flow_v).  replaces python/lucas_kanade_pyramidal.py:66-97 */
+int of_warp_f32(const float* image, const float* flow_u, const float* flow_v, float* out, int height,
+                int width);
+
+/* upsample_flow(flow_u, flow_v, target_shape).  replaces python/lucas_kanade_pyramidal.py:100-138 */
+int of_upsample_flow_f32(const float* coarse_u, const float* coarse_v, float* u, float* v,
+                         int coarse_height, int coarse_width, int target_height, int target_width);
+
+/* lucas_kanade_pyramidal(frame_prev, frame_curr, num_levels, window_size, num_iterations)
+ * for a batch of independent pairs; replaces python/lucas_kanade_pyramidal.py:141-228
+ * (the numeric part; no prints, no plotting).
+ *   iters_executed  optional [batch][levels] (level 0 = coarsest): iterations run before the
+ *                   reference's early exit (mean|du| < 0.01 and mean|dv| < 0.01) fired
+ *   residuals       optional [batch][levels][iterations][2]: mean|du|, mean|dv| */
+int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v, int batch,
+                        int height, int width, int levels, int window, int iterations, int mode,
+                        const double* gauss_weights, int gauss_radius, int* iters_executed,
+                        float* residuals);
+
+/* Fixed-point single-scale LK mirroring the reference RTL's integer datapath
+ * (rtl/unopt/gradient_compute.sv, window_accumulator.sv, flow_solver.sv):
+ * uint8 frames in, int16 S8.7 flow out (real = value / 128), 5x5 window. */
+int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
+                          int batch, int height, int width, int flags);
+
+/* ---- device-buffer entry points (asynchronous on `stream`) --------------------------- */
+int of_lk_single_scale_f32_dev(const float* prev, const float* curr, float* u, float* v, int batch,
+                               int height, int width, int window, int mode, void* stream);
+
+size_t of_lk_pyramidal_workspace_bytes(int batch, int height, int width, int levels, int iterations);
+
+int of_lk_pyramidal_f32_dev(const float* prev, const float* curr, float* u, float* v, int batch,
+                            int height, int width, int levels, int window, int iterations, int mode,
+                            const double* gauss_weights, int gauss_radius, void* workspace,
+                            size_t workspace_bytes, int* iters_executed_dev, float* residuals_dev,
+                            void* stream);
+
+int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
+                              int batch, int height, int width, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OF_B200_H */

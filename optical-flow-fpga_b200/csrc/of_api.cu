@@ -1,0 +1,615 @@
+// C ABI of libof_b200.so (see include/of_b200.h).  Argument checking, device memory for the
+// host-buffer entry points, and the coarse-to-fine driver of the pyramidal path live here;
+// the arithmetic lives in the kernel files.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/of_b200.h"
+#include "of_kernels.h"
+
+using namespace ofb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+std::mutex g_host_mutex;  // host-buffer entry points share one device arena
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define OF_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            cudaGetLastError();                                                                        \
+            return fail(_e == cudaErrorMemoryAllocation ? OF_ERR_OUT_OF_MEMORY : OF_ERR_CUDA,          \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+        }                                                                                              \
+    } while (0)
+
+#define OF_TRY(expr)               \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != OF_OK) return _s; \
+    } while (0)
+
+int need_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(OF_ERR_NO_DEVICE, "no CUDA device is available; this backend has no CPU fallback");
+    }
+    return OF_OK;
+}
+
+struct Counter {
+    int n = 0;
+    ~Counter() { g_launches += n; }
+};
+
+// grow-only device buffers reused by the host-buffer entry points
+struct Arena {
+    std::vector<void*> ptr;
+    std::vector<size_t> cap;
+    int get(size_t idx, size_t bytes, void** out) {
+        if (ptr.size() <= idx) {
+            ptr.resize(idx + 1, nullptr);
+            cap.resize(idx + 1, 0);
+        }
+        if (cap[idx] < bytes) {
+            if (ptr[idx]) cudaFree(ptr[idx]);
+            ptr[idx] = nullptr;
+            cap[idx] = 0;
+            cudaError_t e = cudaMalloc(&ptr[idx], bytes ? bytes : 1);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(OF_ERR_OUT_OF_MEMORY, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+            }
+            cap[idx] = bytes;
+        }
+        *out = ptr[idx];
+        return OF_OK;
+    }
+};
+Arena g_arena;
+cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
+
+int host_streams() {
+    for (int i = 0; i < 3; ++i)
+        if (!g_streams[i]) OF_CUDA(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
+    return OF_OK;
+}
+
+int check_frame(const void* a, const void* b, int H, int W) {
+    if (!a || !b) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (H < 1 || W < 1) return fail(OF_ERR_INVALID_ARGUMENT, "height and width must be >= 1");
+    if ((long long)H * W > (1LL << 31) - 1) return fail(OF_ERR_INVALID_ARGUMENT, "frame too large");
+    return OF_OK;
+}
+
+int check_window(int window) {
+    if (window < 1 || (window & 1) == 0)
+        return fail(OF_ERR_INVALID_ARGUMENT, "window_size must be odd and >= 1");
+    if (!lk_tile_window_supported(window))
+        return fail(OF_ERR_UNSUPPORTED, "window_size > 11 is not supported (NumPy's summation order changes at 128 taps)");
+    return OF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// single scale
+// ---------------------------------------------------------------------------------------
+int single_scale_dev(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int window,
+                     int mode, cudaStream_t stream, Counter& cnt) {
+    if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
+    if (mode == OF_MODE_FAST && lk_march_supported(H, W, window)) {
+        OF_CUDA(launch_lk_march(prev, curr, u, v, batch, H, W, 0, &cnt.n, stream));
+        return OF_OK;
+    }
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in0 = prev;
+    a.in1 = curr;
+    a.out_u = u;
+    a.out_v = v;
+    a.H = H;
+    a.W = W;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        const size_t off = (size_t)b0 * H * W;
+        TileArgs c = a;
+        c.in0 = prev + off;
+        c.in1 = curr + off;
+        c.out_u = u + off;
+        c.out_v = v + off;
+        OF_CUDA(launch_lk_tile(SRC_FRAMES, window, c, nb, &cnt.n, stream));
+    }
+    return OF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// pyramidal driver
+// ---------------------------------------------------------------------------------------
+struct PyrPlan {
+    int L = 0;
+    std::vector<int> h, w;                      // k = 0 finest ... L-1 coarsest
+    std::vector<size_t> prev_off, curr_off;      // k >= 1
+    std::vector<size_t> au_off, av_off, bu_off, bv_off;  // flow ping-pong (A of k = 0 is the caller's u, v)
+    size_t partial_off = 0, sel_off = 0, done_off = 0, total = 0;
+    int max_blocks = 0;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
+    if (levels < 1 || levels > 16) return fail(OF_ERR_INVALID_ARGUMENT, "num_levels must be in 1..16");
+    p.L = levels;
+    p.h.assign(levels, 0);
+    p.w.assign(levels, 0);
+    p.h[0] = H;
+    p.w[0] = W;
+    for (int k = 1; k < levels; ++k) {
+        p.h[k] = p.h[k - 1] / 2;  // int(h * 0.5)
+        p.w[k] = p.w[k - 1] / 2;
+        if (p.h[k] < 1 || p.w[k] < 1) return fail(OF_ERR_INVALID_ARGUMENT, "frame too small for this many pyramid levels");
+    }
+    size_t off = 0;
+    p.prev_off.assign(levels, 0);
+    p.curr_off.assign(levels, 0);
+    p.au_off.assign(levels, 0);
+    p.av_off.assign(levels, 0);
+    p.bu_off.assign(levels, 0);
+    p.bv_off.assign(levels, 0);
+    p.max_blocks = 0;
+    for (int k = 0; k < levels; ++k) {
+        const size_t bytes = align_up((size_t)batch * p.h[k] * p.w[k] * sizeof(float));
+        if (k >= 1) {
+            p.prev_off[k] = off; off += bytes;
+            p.curr_off[k] = off; off += bytes;
+            p.au_off[k] = off; off += bytes;
+            p.av_off[k] = off; off += bytes;
+        }
+        p.bu_off[k] = off; off += bytes;
+        p.bv_off[k] = off; off += bytes;
+        const int nb = lk_tile_blocks_per_pair(p.h[k], p.w[k]);
+        if (nb > p.max_blocks) p.max_blocks = nb;
+    }
+    p.partial_off = off; off += align_up((size_t)batch * p.max_blocks * 2 * sizeof(double));
+    p.sel_off = off; off += align_up((size_t)levels * batch * sizeof(int));
+    p.done_off = off; off += align_up((size_t)levels * batch * sizeof(int));
+    p.total = off;
+    return OF_OK;
+}
+
+int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int levels,
+                  int window, int iterations, int mode, const double* gw, int radius, void* workspace, size_t ws_bytes,
+                  int* iters_dev, float* resid_dev, cudaStream_t stream, Counter& cnt) {
+    (void)mode;  // both modes run the reference-order kernels on this path for now
+    if (iterations < 0) return fail(OF_ERR_INVALID_ARGUMENT, "num_iterations must be >= 0");
+    if (batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "at most 65535 pairs per call on the device entry point");
+    if (levels > 1 && (!gw || radius < 0 || radius > OF_MAX_GAUSS_RADIUS))
+        return fail(OF_ERR_INVALID_ARGUMENT, "gaussian weights missing or radius out of range");
+    PyrPlan p;
+    OF_TRY(make_plan(batch, H, W, levels, p));
+    if (!workspace || ws_bytes < p.total) return fail(OF_ERR_INVALID_ARGUMENT, "workspace too small");
+    char* ws = static_cast<char*>(workspace);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    int* sel = reinterpret_cast<int*>(ws + p.sel_off);
+    int* done = reinterpret_cast<int*>(ws + p.done_off);
+    double* partial = reinterpret_cast<double*>(ws + p.partial_off);
+
+    OF_CUDA(cudaMemsetAsync(ws + p.sel_off, 0, p.total - p.sel_off, stream));
+    if (iters_dev) OF_CUDA(cudaMemsetAsync(iters_dev, 0, (size_t)batch * levels * sizeof(int), stream));
+    if (resid_dev && iterations > 0)
+        OF_CUDA(cudaMemsetAsync(resid_dev, 0, (size_t)batch * levels * iterations * 2 * sizeof(float), stream));
+
+    // Gaussian pyramids of both frames, fine -> coarse
+    std::vector<const float*> lp(levels), lc(levels);
+    lp[0] = prev;
+    lc[0] = curr;
+    for (int k = 1; k < levels; ++k) {
+        OF_CUDA(launch_pyramid_down(lp[k - 1], F(p.prev_off[k]), batch, p.h[k - 1], p.w[k - 1], p.h[k], p.w[k], gw,
+                                    radius, &cnt.n, stream));
+        OF_CUDA(launch_pyramid_down(lc[k - 1], F(p.curr_off[k]), batch, p.h[k - 1], p.w[k - 1], p.h[k], p.w[k], gw,
+                                    radius, &cnt.n, stream));
+        lp[k] = F(p.prev_off[k]);
+        lc[k] = F(p.curr_off[k]);
+    }
+    auto flowA_u = [&](int k) { return k == 0 ? u : F(p.au_off[k]); };
+    auto flowA_v = [&](int k) { return k == 0 ? v : F(p.av_off[k]); };
+
+    // zero flow at the coarsest level
+    const int kc = levels - 1;
+    const size_t coarse_bytes = (size_t)batch * p.h[kc] * p.w[kc] * sizeof(float);
+    OF_CUDA(cudaMemsetAsync(flowA_u(kc), 0, coarse_bytes, stream));
+    OF_CUDA(cudaMemsetAsync(flowA_v(kc), 0, coarse_bytes, stream));
+
+    for (int k = kc; k >= 0; --k) {
+        const int ref_level = kc - k;  // the reference counts levels from the coarsest
+        int* sel_k = sel + (size_t)k * batch;
+        int* done_k = done + (size_t)k * batch;
+        if (k < kc) {
+            OF_CUDA(launch_upsample_flow(flowA_u(k + 1), flowA_v(k + 1), F(p.bu_off[k + 1]), F(p.bv_off[k + 1]),
+                                         sel + (size_t)(k + 1) * batch, flowA_u(k), flowA_v(k), batch, p.h[k + 1],
+                                         p.w[k + 1], p.h[k], p.w[k], &cnt.n, stream));
+        }
+        for (int it = 0; it < iterations; ++it) {
+            TileArgs a;
+            memset(&a, 0, sizeof(a));
+            a.in0 = lp[k];
+            a.in1 = lc[k];
+            a.flow_u[0] = flowA_u(k);
+            a.flow_v[0] = flowA_v(k);
+            a.flow_u[1] = F(p.bu_off[k]);
+            a.flow_v[1] = F(p.bv_off[k]);
+            a.sel = sel_k;
+            a.done = done_k;
+            a.partial = partial;
+            a.H = p.h[k];
+            a.W = p.w[k];
+            OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
+            IterFinalizeArgs f;
+            f.partial = partial;
+            f.blocks_per_pair = lk_tile_blocks_per_pair(p.h[k], p.w[k]);
+            f.H = p.h[k];
+            f.W = p.w[k];
+            f.sel = sel_k;
+            f.done = done_k;
+            f.iters_executed = iters_dev ? iters_dev + ref_level : nullptr;
+            f.iters_pair_stride = levels;
+            f.residuals = resid_dev ? resid_dev + (size_t)ref_level * iterations * 2 : nullptr;
+            f.resid_pair_stride = (size_t)levels * iterations * 2;
+            f.iteration = it;
+            OF_CUDA(launch_iter_finalize(f, batch, &cnt.n, stream));
+        }
+    }
+    // the finest level's current buffer -> caller's (u, v) (no-op for pairs already there)
+    OF_CUDA(launch_select_copy(u, v, F(p.bu_off[0]), F(p.bv_off[0]), sel, u, v, batch, (size_t)H * W, &cnt.n, stream));
+    return OF_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+// exported C ABI
+// =======================================================================================
+extern "C" {
+
+int of_version(void) { return 100; }
+
+const char* of_last_error(void) { return g_err.c_str(); }
+
+int of_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int of_set_device(int ordinal) {
+    OF_TRY(need_device());
+    OF_CUDA(cudaSetDevice(ordinal));
+    return OF_OK;
+}
+
+long long of_kernel_launches(void) { return g_launches.load(); }
+
+int of_host_alloc_pinned(void** ptr, size_t bytes) {
+    if (!ptr) return fail(OF_ERR_INVALID_ARGUMENT, "null pointer");
+    OF_TRY(need_device());
+    OF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return OF_OK;
+}
+
+int of_host_free_pinned(void* ptr) {
+    if (ptr) OF_CUDA(cudaFreeHost(ptr));
+    return OF_OK;
+}
+
+int of_lk_single_scale_f32_dev(const float* prev, const float* curr, float* u, float* v, int batch, int height,
+                               int width, int window, int mode, void* stream) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    OF_TRY(check_window(window));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    Counter cnt;
+    return single_scale_dev(prev, curr, u, v, batch, height, width, window, mode, static_cast<cudaStream_t>(stream), cnt);
+}
+
+int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float* v, int batch, int height, int width,
+                           int window, int mode) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    OF_TRY(check_window(window));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t plane = (size_t)height * width;
+    // chunks of <= 128 MiB per array, three in flight: H2D of chunk i+1 and D2H of chunk i-1
+    // overlap the kernel of chunk i (needs pinned host memory to actually overlap)
+    size_t per_chunk = (128u << 20) / (plane * sizeof(float));
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > (size_t)batch) per_chunk = batch;
+    const size_t chunk_bytes = per_chunk * plane * sizeof(float);
+    const int n_chunks = (int)((batch + per_chunk - 1) / per_chunk);
+    const int slots = n_chunks < 3 ? n_chunks : 3;
+    float* d[3][4];
+    for (int s = 0; s < slots; ++s)
+        for (int j = 0; j < 4; ++j) OF_TRY(g_arena.get(s * 4 + j, chunk_bytes, reinterpret_cast<void**>(&d[s][j])));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % slots;
+        cudaStream_t st = g_streams[s];
+        const size_t b0 = (size_t)c * per_chunk;
+        const int nb = (int)((size_t)batch - b0 < per_chunk ? (size_t)batch - b0 : per_chunk);
+        const size_t bytes = (size_t)nb * plane * sizeof(float);
+        OF_CUDA(cudaMemcpyAsync(d[s][0], prev + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
+        OF_CUDA(cudaMemcpyAsync(d[s][1], curr + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
+        OF_TRY(single_scale_dev(d[s][0], d[s][1], d[s][2], d[s][3], nb, height, width, window, mode, st, cnt));
+        OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d[s][2], bytes, cudaMemcpyDeviceToHost, st));
+        OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d[s][3], bytes, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(g_streams[s]));
+    return OF_OK;
+}
+
+int of_gradients_f32(const float* prev, const float* curr, float* ix, float* iy, float* it, int height, int width) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(ix, iy, height, width));
+    if (!it) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t bytes = (size_t)height * width * sizeof(float);
+    float* d[5];
+    for (int j = 0; j < 5; ++j) OF_TRY(g_arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(d[0], prev, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(d[1], curr, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(launch_gradients(d[0], d[1], d[2], d[3], d[4], 1, height, width, &cnt.n, st));
+    OF_CUDA(cudaMemcpyAsync(ix, d[2], bytes, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaMemcpyAsync(iy, d[3], bytes, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaMemcpyAsync(it, d[4], bytes, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+int of_lk_from_gradients_f32(const float* ix, const float* iy, const float* it, float* u, float* v, int height,
+                             int width, int window) {
+    OF_TRY(check_frame(ix, iy, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    if (!it) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    OF_TRY(check_window(window));
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t bytes = (size_t)height * width * sizeof(float);
+    float* d[5];
+    for (int j = 0; j < 5; ++j) OF_TRY(g_arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(d[0], ix, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(d[1], iy, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(d[2], it, bytes, cudaMemcpyHostToDevice, st));
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in0 = d[0];
+    a.in1 = d[1];
+    a.in2 = d[2];
+    a.out_u = d[3];
+    a.out_v = d[4];
+    a.H = height;
+    a.W = width;
+    OF_CUDA(launch_lk_tile(SRC_GRADS, window, a, 1, &cnt.n, st));
+    OF_CUDA(cudaMemcpyAsync(u, d[3], bytes, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaMemcpyAsync(v, d[4], bytes, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+int of_pyramid_down_f32(const float* src, float* dst, int height, int width, int out_height, int out_width,
+                        const double* weights, int radius) {
+    OF_TRY(check_frame(src, dst, height, width));
+    if (out_height < 1 || out_width < 1) return fail(OF_ERR_INVALID_ARGUMENT, "output size must be >= 1");
+    if (!weights || radius < 0 || radius > OF_MAX_GAUSS_RADIUS)
+        return fail(OF_ERR_INVALID_ARGUMENT, "gaussian weights missing or radius out of range");
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t ib = (size_t)height * width * sizeof(float), ob = (size_t)out_height * out_width * sizeof(float);
+    float *ds, *dd;
+    OF_TRY(g_arena.get(0, ib, reinterpret_cast<void**>(&ds)));
+    OF_TRY(g_arena.get(1, ob, reinterpret_cast<void**>(&dd)));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(ds, src, ib, cudaMemcpyHostToDevice, st));
+    OF_CUDA(launch_pyramid_down(ds, dd, 1, height, width, out_height, out_width, weights, radius, &cnt.n, st));
+    OF_CUDA(cudaMemcpyAsync(dst, dd, ob, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+int of_warp_f32(const float* image, const float* flow_u, const float* flow_v, float* out, int height, int width) {
+    OF_TRY(check_frame(image, out, height, width));
+    OF_TRY(check_frame(flow_u, flow_v, height, width));
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t bytes = (size_t)height * width * sizeof(float);
+    float* d[4];
+    for (int j = 0; j < 4; ++j) OF_TRY(g_arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(d[0], image, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(d[1], flow_u, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(d[2], flow_v, bytes, cudaMemcpyHostToDevice, st));
+    OF_CUDA(launch_warp(d[0], d[1], d[2], d[3], 1, height, width, &cnt.n, st));
+    OF_CUDA(cudaMemcpyAsync(out, d[3], bytes, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+int of_upsample_flow_f32(const float* coarse_u, const float* coarse_v, float* u, float* v, int coarse_height,
+                         int coarse_width, int target_height, int target_width) {
+    OF_TRY(check_frame(coarse_u, coarse_v, coarse_height, coarse_width));
+    OF_TRY(check_frame(u, v, target_height, target_width));
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t cb = (size_t)coarse_height * coarse_width * sizeof(float);
+    const size_t tb = (size_t)target_height * target_width * sizeof(float);
+    float* d[4];
+    OF_TRY(g_arena.get(0, cb, reinterpret_cast<void**>(&d[0])));
+    OF_TRY(g_arena.get(1, cb, reinterpret_cast<void**>(&d[1])));
+    OF_TRY(g_arena.get(2, tb, reinterpret_cast<void**>(&d[2])));
+    OF_TRY(g_arena.get(3, tb, reinterpret_cast<void**>(&d[3])));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(d[0], coarse_u, cb, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(d[1], coarse_v, cb, cudaMemcpyHostToDevice, st));
+    OF_CUDA(launch_upsample_flow(d[0], d[1], nullptr, nullptr, nullptr, d[2], d[3], 1, coarse_height, coarse_width,
+                                 target_height, target_width, &cnt.n, st));
+    OF_CUDA(cudaMemcpyAsync(u, d[2], tb, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaMemcpyAsync(v, d[3], tb, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+size_t of_lk_pyramidal_workspace_bytes(int batch, int height, int width, int levels, int iterations) {
+    (void)iterations;
+    PyrPlan p;
+    if (batch < 1 || height < 1 || width < 1 || make_plan(batch, height, width, levels, p) != OF_OK) return 0;
+    return p.total;
+}
+
+int of_lk_pyramidal_f32_dev(const float* prev, const float* curr, float* u, float* v, int batch, int height, int width,
+                            int levels, int window, int iterations, int mode, const double* gauss_weights,
+                            int gauss_radius, void* workspace, size_t workspace_bytes, int* iters_executed_dev,
+                            float* residuals_dev, void* stream) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    OF_TRY(check_window(window));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    Counter cnt;
+    return pyramidal_dev(prev, curr, u, v, batch, height, width, levels, window, iterations, mode, gauss_weights,
+                         gauss_radius, workspace, workspace_bytes, iters_executed_dev, residuals_dev,
+                         static_cast<cudaStream_t>(stream), cnt);
+}
+
+int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v, int batch, int height, int width,
+                        int levels, int window, int iterations, int mode, const double* gauss_weights,
+                        int gauss_radius, int* iters_executed, float* residuals) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    OF_TRY(check_window(window));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (iterations < 0) return fail(OF_ERR_INVALID_ARGUMENT, "num_iterations must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t plane = (size_t)height * width;
+    // pairs per pass: keep frames + workspace of one pass around 2 GiB
+    size_t per_pass = (size_t)(256u << 20) / (plane * sizeof(float));
+    if (per_pass < 1) per_pass = 1;
+    if (per_pass > (size_t)batch) per_pass = batch;
+    if (per_pass > 65535) per_pass = 65535;
+    PyrPlan plan;
+    OF_TRY(make_plan((int)per_pass, height, width, levels, plan));
+    const size_t fb = per_pass * plane * sizeof(float);
+    float* d[4];
+    for (int j = 0; j < 4; ++j) OF_TRY(g_arena.get(j, fb, reinterpret_cast<void**>(&d[j])));
+    void* ws;
+    OF_TRY(g_arena.get(4, plan.total, &ws));
+    int* d_iters = nullptr;
+    float* d_res = nullptr;
+    const size_t ib = per_pass * levels * sizeof(int);
+    const size_t rb = per_pass * levels * (size_t)(iterations > 0 ? iterations : 1) * 2 * sizeof(float);
+    if (iters_executed) OF_TRY(g_arena.get(5, ib, reinterpret_cast<void**>(&d_iters)));
+    if (residuals) OF_TRY(g_arena.get(6, rb, reinterpret_cast<void**>(&d_res)));
+    cudaStream_t st = g_streams[0];
+    for (size_t b0 = 0; b0 < (size_t)batch; b0 += per_pass) {
+        const int nb = (int)((size_t)batch - b0 < per_pass ? (size_t)batch - b0 : per_pass);
+        const size_t bytes = (size_t)nb * plane * sizeof(float);
+        OF_CUDA(cudaMemcpyAsync(d[0], prev + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
+        OF_CUDA(cudaMemcpyAsync(d[1], curr + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
+        PyrPlan pp;
+        OF_TRY(make_plan(nb, height, width, levels, pp));
+        OF_TRY(pyramidal_dev(d[0], d[1], d[2], d[3], nb, height, width, levels, window, iterations, mode,
+                             gauss_weights, gauss_radius, ws, pp.total, d_iters, d_res, st, cnt));
+        OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d[2], bytes, cudaMemcpyDeviceToHost, st));
+        OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d[3], bytes, cudaMemcpyDeviceToHost, st));
+        if (iters_executed)
+            OF_CUDA(cudaMemcpyAsync(iters_executed + b0 * levels, d_iters, (size_t)nb * levels * sizeof(int),
+                                    cudaMemcpyDeviceToHost, st));
+        if (residuals && iterations > 0)
+            OF_CUDA(cudaMemcpyAsync(residuals + b0 * levels * iterations * 2, d_res,
+                                    (size_t)nb * levels * iterations * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        OF_CUDA(cudaStreamSynchronize(st));
+    }
+    return OF_OK;
+}
+
+int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int height,
+                              int width, int flags, void* stream) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    Counter cnt;
+    const size_t plane = (size_t)height * width;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        OF_CUDA(launch_lk_fixed(prev + b0 * plane, curr + b0 * plane, u + b0 * plane, v + b0 * plane, nb, height, width,
+                                (flags & OF_FX_MIRROR_AVG_QUIRK) ? 1 : 0, &cnt.n, static_cast<cudaStream_t>(stream)));
+    }
+    return OF_OK;
+}
+
+int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int height,
+                          int width, int flags) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    const size_t n = (size_t)batch * height * width;
+    uint8_t *dp, *dc;
+    int16_t *du, *dv;
+    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&dp)));
+    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dc)));
+    OF_TRY(g_arena.get(2, n * 2, reinterpret_cast<void**>(&du)));
+    OF_TRY(g_arena.get(3, n * 2, reinterpret_cast<void**>(&dv)));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(dp, prev, n, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(dc, curr, n, cudaMemcpyHostToDevice, st));
+    OF_TRY(of_lk_single_scale_fx_dev(dp, dc, du, dv, batch, height, width, flags, st));
+    OF_CUDA(cudaMemcpyAsync(u, du, n * 2, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaMemcpyAsync(v, dv, n * 2, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+}  // extern "C"

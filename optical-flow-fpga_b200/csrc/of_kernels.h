@@ -1,0 +1,84 @@
+// Internal launch interface between the C-ABI layer (of_api.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ofb {
+
+// ---- K1 fast: warp-marching fused single-scale LK (lk_march.cu) ------------------------
+struct MarchArgs {
+    const float* prev;
+    const float* curr;
+    float* u;
+    float* v;
+    int H, W;
+    int n_strips, n_bands, band_rows;
+    long long n_units;
+};
+bool lk_march_supported(int H, int W, int window);
+// force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
+cudaError_t launch_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W,
+                            int force_path, int* launches, cudaStream_t stream);
+
+// ---- K1/K3 exact: tile kernel in the reference's operation order (lk_tile.cu) ----------
+enum TileSource { SRC_FRAMES = 0, SRC_WARP = 1, SRC_GRADS = 2 };
+struct TileArgs {
+    // SRC_FRAMES: in0 = prev, in1 = curr.  SRC_WARP: in0 = prev level, in1 = curr level (gathered
+    // through the flow).  SRC_GRADS: in0 = Ix, in1 = Iy, in2 = It.
+    const float* in0;
+    const float* in1;
+    const float* in2;
+    // SRC_WARP only: ping-pong flow buffers; sel[pair] says which one is current (0 = A).
+    float* flow_u[2];
+    float* flow_v[2];
+    const int* sel;    // nullable: A is the input, B the output
+    const int* done;   // nullable: pairs whose level has converged are skipped
+    double* partial;   // [pair][blocks_per_pair][2] sums of |du|, |dv| (SRC_WARP)
+    // SRC_FRAMES / SRC_GRADS outputs
+    float* out_u;
+    float* out_v;
+    int H, W;
+};
+cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream);
+int lk_tile_blocks_per_pair(int H, int W);
+bool lk_tile_window_supported(int window);
+
+// after one refinement iteration: reduce the per-block partial sums, decide convergence,
+// flip the ping-pong selector (lucas_kanade_pyramidal.py:213-223)
+struct IterFinalizeArgs {
+    const double* partial;
+    int blocks_per_pair;
+    int H, W;
+    int* sel;
+    int* done;
+    int* iters_executed;        // nullable; element of pair b is iters_executed[b * iters_pair_stride]
+    int iters_pair_stride;
+    float* residuals;           // nullable; (mean|du|, mean|dv|) of pair b, iteration i at
+    size_t resid_pair_stride;   //   residuals[b * resid_pair_stride + 2 * i]
+    int iteration;
+};
+cudaError_t launch_iter_finalize(const IterFinalizeArgs& a, int batch, int* launches, cudaStream_t stream);
+
+// ---- helper kernels (pyramid.cu) -------------------------------------------------------
+cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, float* iy, float* it, int batch, int H,
+                             int W, int* launches, cudaStream_t stream);
+// fused Gaussian (separable, float64 accumulate, float32 store per axis, reflect) + bilinear
+// resample on the np.linspace grid (lucas_kanade_pyramidal.py:44-59)
+cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
+                                const double* weights, int radius, int* launches, cudaStream_t stream);
+cudaError_t launch_warp(const float* img, const float* fu, const float* fv, float* out, int batch, int H, int W,
+                        int* launches, cudaStream_t stream);
+// coarse flow (selected ping-pong buffer) -> fine grid, scaled (lucas_kanade_pyramidal.py:100-138)
+cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
+                                 const int* sel, float* fu, float* fv, int batch, int ch, int cw, int th, int tw,
+                                 int* launches, cudaStream_t stream);
+// copy the selected ping-pong buffer of every pair to the caller's output
+cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1, const float* v1, const int* sel,
+                               float* out_u, float* out_v, int batch, size_t n, int* launches, cudaStream_t stream);
+
+// ---- fixed-point mode (lk_fixed.cu) ----------------------------------------------------
+cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,
+                            int mirror_avg_quirk, int* launches, cudaStream_t stream);
+
+}  // namespace ofb

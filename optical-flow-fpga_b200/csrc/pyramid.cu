@@ -1,0 +1,291 @@
+// K2 / K4 and the stand-alone helpers of the pyramidal path.
+//
+//   pyramid_down   one level of build_gaussian_pyramid   (lucas_kanade_pyramidal.py:44-59)
+//   warp           warp_image                            (lucas_kanade_pyramidal.py:66-97)
+//   upsample_flow  upsample_flow                         (lucas_kanade_pyramidal.py:100-138)
+//   gradients      compute_gradients                     (lucas_kanade_core.py:15-45)
+//
+// SciPy semantics that are mirrored (pinned by tests/golden):
+//   gaussian_filter: per axis float64 accumulate in SciPy's symmetric-kernel order
+//   (centre tap, then (x[c-k] + x[c+k]) * w[k] for k = radius..1), float32 store after
+//   each axis, rows (axis 0) first, 'reflect' boundary.  map_coordinates(order=1,
+//   mode="constant"): float64 coordinates and blend, outside -> exactly 0.
+#include <cuda_runtime.h>
+
+#include "of_common.cuh"
+#include "of_kernels.h"
+
+namespace ofb {
+
+// ---------------------------------------------------------------------------------------
+// compute_gradients
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gradients_kernel(const float* __restrict__ prev, const float* __restrict__ curr,
+                                                         float* __restrict__ ix, float* __restrict__ iy,
+                                                         float* __restrict__ it, int H, int W) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)H * W;
+    const float* p = prev + blockIdx.z * plane;
+    const float* c = curr + blockIdx.z * plane;
+    const float kx[3][3] = {{-0.125f, 0.0f, 0.125f}, {-0.25f, 0.0f, 0.25f}, {-0.125f, 0.0f, 0.125f}};
+    const float ky[3][3] = {{-0.125f, -0.25f, -0.125f}, {0.0f, 0.0f, 0.0f}, {0.125f, 0.25f, 0.125f}};
+    float ax = 0.0f, ay = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int yy = clampi(y + 1 - j, 0, H - 1), xx = clampi(x + 1 - k, 0, W - 1);
+            const size_t o = (size_t)yy * W + xx;
+            const float avg = fmul(fadd(__ldg(p + o), __ldg(c + o)), 0.5f);
+            ax = fadd(ax, fmul(avg, kx[j][k]));
+            ay = fadd(ay, fmul(avg, ky[j][k]));
+        }
+    const size_t o = (size_t)y * W + x;
+    ix[blockIdx.z * plane + o] = ax;
+    iy[blockIdx.z * plane + o] = ay;
+    it[blockIdx.z * plane + o] = fsub(__ldg(p + o), __ldg(c + o));
+}
+
+cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, float* iy, float* it, int batch, int H,
+                             int W, int* launches, cudaStream_t stream) {
+    if (launches) *launches += 1;
+    dim3 grid((W + 63) / 64, (H + 3) / 4, batch);
+    gradients_kernel<<<grid, 256, 0, stream>>>(prev, curr, ix, iy, it, H, W);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// fused Gaussian blur + bilinear decimation
+// ---------------------------------------------------------------------------------------
+constexpr int PYR_MAX_RADIUS = 16;
+constexpr int PYR_RMAX = 40;  // smoothed rows a CTA may need
+constexpr int PYR_CMAX = 72;  // smoothed columns a CTA may need
+
+struct PyrArgs {
+    const float* src;
+    float* dst;
+    int H, W, oh, ow;
+    int tile_h, tile_w;  // coarse pixels per CTA
+    int radius;
+    double step_y, step_x;
+    double w[2 * PYR_MAX_RADIUS + 1];
+};
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    // scipy 'reflect': (d c b a | a b c d | d c b a), any overhang
+    const int period = 2 * n;
+    int m = i % period;
+    if (m < 0) m += period;
+    return m >= n ? period - 1 - m : m;
+}
+
+__global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
+    extern __shared__ float smem[];
+    const int H = a.H, W = a.W, r = a.radius;
+    const float* src = a.src + (size_t)blockIdx.z * H * W;
+    float* dst = a.dst + (size_t)blockIdx.z * a.oh * a.ow;
+
+    const int i0 = blockIdx.y * a.tile_h, j0 = blockIdx.x * a.tile_w;
+    const int i1 = min(i0 + a.tile_h, a.oh) - 1, j1 = min(j0 + a.tile_w, a.ow) - 1;
+    // fine rows / columns whose smoothed value the bilinear taps of this tile can touch
+    const int fy_lo = (int)floor(linspace_coord(i0, a.oh, H, a.step_y));
+    const int fy_hi = min((int)floor(linspace_coord(i1, a.oh, H, a.step_y)) + 1, H - 1);
+    const int fx_lo = (int)floor(linspace_coord(j0, a.ow, W, a.step_x));
+    const int fx_hi = min((int)floor(linspace_coord(j1, a.ow, W, a.step_x)) + 1, W - 1);
+    const int R = fy_hi - fy_lo + 1, C = fx_hi - fx_lo + 1;
+    const int IW = C + 2 * r, IH = R + 2 * r;
+
+    float* img = smem;            // [IH][IW]   source with reflected halo
+    float* tmp = img + IH * IW;   // [R][IW]    after the axis-0 pass (float32)
+    float* smo = tmp + R * IW;    // [R][C]     after the axis-1 pass (float32)
+
+    for (int i = threadIdx.x; i < IH * IW; i += 256) {
+        const int y = reflect_index(fy_lo - r + i / IW, H);
+        const int x = reflect_index(fx_lo - r + i % IW, W);
+        img[i] = __ldg(src + (size_t)y * W + x);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * IW; i += 256) {
+        const int rr = i / IW, cc = i % IW;
+        const float* col = img + (rr + r) * IW + cc;
+        double acc = dmul((double)col[0], a.w[r]);
+        for (int ii = -r; ii < 0; ++ii)
+            acc = dadd(acc, dmul(dadd((double)col[ii * IW], (double)col[-ii * IW]), a.w[ii + r]));
+        tmp[i] = (float)acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * C; i += 256) {
+        const int rr = i / C, cc = i % C;
+        const float* row = tmp + rr * IW + cc + r;
+        double acc = dmul((double)row[0], a.w[r]);
+        for (int ii = -r; ii < 0; ++ii)
+            acc = dadd(acc, dmul(dadd((double)row[ii], (double)row[-ii]), a.w[ii + r]));
+        smo[i] = (float)acc;
+    }
+    __syncthreads();
+    const int th = i1 - i0 + 1, tw = j1 - j0 + 1;
+    for (int o = threadIdx.x; o < th * tw; o += 256) {
+        const int i = i0 + o / tw, j = j0 + o % tw;
+        const double y = linspace_coord(i, a.oh, H, a.step_y);
+        const double x = linspace_coord(j, a.ow, W, a.step_x);
+        const double fy0 = floor(y), fx0 = floor(x);
+        const double fy = dsub(y, fy0), fx = dsub(x, fx0);
+        const int y0 = (int)fy0, x0 = (int)fx0;
+        // the tap beyond the last row/column has weight exactly 0 (SciPy mirrors its index)
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const double wy0 = dsub(1.0, fy), wx0 = dsub(1.0, fx);
+        const float* s0 = smo + (y0 - fy_lo) * C - fx_lo;
+        const float* s1 = smo + (y1 - fy_lo) * C - fx_lo;
+        double t = 0.0;
+        t = dadd(t, dmul(dmul((double)s0[x0], wy0), wx0));
+        t = dadd(t, dmul(dmul((double)s0[x1], wy0), fx));
+        t = dadd(t, dmul(dmul((double)s1[x0], fy), wx0));
+        t = dadd(t, dmul(dmul((double)s1[x1], fy), fx));
+        dst[(size_t)i * a.ow + j] = (float)t;
+    }
+}
+
+static int pyr_tile_extent(int limit, double step) {
+    // largest n with ceil((n - 1) * step) + 2 <= limit, capped
+    int n = (int)((limit - 3) / step) + 1;
+    if (n < 1) n = 1;
+    return n;
+}
+
+cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
+                                const double* weights, int radius, int* launches, cudaStream_t stream) {
+    if (radius < 0 || radius > PYR_MAX_RADIUS || oh < 1 || ow < 1 || batch > 65535) return cudaErrorInvalidValue;
+    PyrArgs a;
+    a.src = src;
+    a.dst = dst;
+    a.H = H;
+    a.W = W;
+    a.oh = oh;
+    a.ow = ow;
+    a.radius = radius;
+    a.step_y = oh > 1 ? (double)(H - 1) / (double)(oh - 1) : 0.0;  // np.linspace step
+    a.step_x = ow > 1 ? (double)(W - 1) / (double)(ow - 1) : 0.0;
+    for (int i = 0; i < 2 * radius + 1; ++i) a.w[i] = weights[i];
+    a.tile_h = a.step_y > 0 ? pyr_tile_extent(PYR_RMAX, a.step_y) : 16;
+    a.tile_w = a.step_x > 0 ? pyr_tile_extent(PYR_CMAX, a.step_x) : 32;
+    if (a.tile_h > 16) a.tile_h = 16;
+    if (a.tile_w > 32) a.tile_w = 32;
+    const int IHmax = PYR_RMAX + 2 * radius, IWmax = PYR_CMAX + 2 * radius;
+    const size_t smem = (size_t)(IHmax * IWmax + PYR_RMAX * IWmax + PYR_RMAX * PYR_CMAX) * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e =
+            cudaFuncSetAttribute(pyramid_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
+    if (launches) *launches += 1;
+    dim3 grid((ow + a.tile_w - 1) / a.tile_w, (oh + a.tile_h - 1) / a.tile_h, batch);
+    pyramid_down_kernel<<<grid, 256, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// warp_image / upsample_flow / select-copy
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ img, const float* __restrict__ fu,
+                                                    const float* __restrict__ fv, float* __restrict__ out, int H,
+                                                    int W) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)H * W, o = blockIdx.z * plane + (size_t)y * W + x;
+    const double yw = dadd((double)y, (double)__ldg(fv + o));
+    const double xw = dadd((double)x, (double)__ldg(fu + o));
+    out[o] = bilinear_f64(img + blockIdx.z * plane, H, W, yw, xw);
+}
+
+cudaError_t launch_warp(const float* img, const float* fu, const float* fv, float* out, int batch, int H, int W,
+                        int* launches, cudaStream_t stream) {
+    if (launches) *launches += 1;
+    dim3 grid((W + 63) / 64, (H + 3) / 4, batch);
+    warp_kernel<<<grid, 256, 0, stream>>>(img, fu, fv, out, H, W);
+    return cudaGetLastError();
+}
+
+struct UpArgs {
+    const float* cu[2];
+    const float* cv[2];
+    const int* sel;
+    float* fu;
+    float* fv;
+    int ch, cw, th, tw;
+    double step_y, step_x;
+    float scale_y, scale_x;
+};
+
+__global__ void __launch_bounds__(256) upsample_flow_kernel(UpArgs a) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= a.tw || y >= a.th) return;
+    const int pair = blockIdx.z;
+    const int cur = a.sel ? a.sel[pair] : 0;
+    const size_t cplane = (size_t)a.ch * a.cw;
+    const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
+    const double xc = linspace_coord(x, a.tw, a.cw, a.step_x);
+    const float u = bilinear_f64(a.cu[cur] + pair * cplane, a.ch, a.cw, yc, xc);
+    const float v = bilinear_f64(a.cv[cur] + pair * cplane, a.ch, a.cw, yc, xc);
+    const size_t o = (size_t)pair * a.th * a.tw + (size_t)y * a.tw + x;
+    a.fu[o] = fmul(u, a.scale_x);  // flow scales with the resolution, float32 multiply
+    a.fv[o] = fmul(v, a.scale_y);
+}
+
+cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
+                                 const int* sel, float* fu, float* fv, int batch, int ch, int cw, int th, int tw,
+                                 int* launches, cudaStream_t stream) {
+    UpArgs a;
+    a.cu[0] = cu0;
+    a.cv[0] = cv0;
+    a.cu[1] = cu1 ? cu1 : cu0;
+    a.cv[1] = cv1 ? cv1 : cv0;
+    a.sel = sel;
+    a.fu = fu;
+    a.fv = fv;
+    a.ch = ch;
+    a.cw = cw;
+    a.th = th;
+    a.tw = tw;
+    a.step_y = th > 1 ? (double)(ch - 1) / (double)(th - 1) : 0.0;
+    a.step_x = tw > 1 ? (double)(cw - 1) / (double)(tw - 1) : 0.0;
+    a.scale_y = (float)((double)th / (double)ch);
+    a.scale_x = (float)((double)tw / (double)cw);
+    if (launches) *launches += 1;
+    dim3 grid((tw + 63) / 64, (th + 3) / 4, batch);
+    upsample_flow_kernel<<<grid, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) select_copy_kernel(const float* __restrict__ u0, const float* __restrict__ v0,
+                                                           const float* __restrict__ u1, const float* __restrict__ v1,
+                                                           const int* __restrict__ sel, float* __restrict__ out_u,
+                                                           float* __restrict__ out_v, size_t n) {
+    const int pair = blockIdx.y;
+    const int cur = sel ? sel[pair] : 0;
+    const float* su = (cur ? u1 : u0) + pair * n;
+    const float* sv = (cur ? v1 : v0) + pair * n;
+    if (su == out_u + pair * n) return;  // already in place
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        out_u[pair * n + i] = su[i];
+        out_v[pair * n + i] = sv[i];
+    }
+}
+
+cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1, const float* v1, const int* sel,
+                               float* out_u, float* out_v, int batch, size_t n, int* launches, cudaStream_t stream) {
+    if (launches) *launches += 1;
+    unsigned bx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 4096) bx = 4096;
+    dim3 grid(bx, batch);
+    select_copy_kernel<<<grid, 256, 0, stream>>>(u0, v0, u1, v1, sel, out_u, out_v, n);
+    return cudaGetLastError();
+}
+
+}  // namespace ofb

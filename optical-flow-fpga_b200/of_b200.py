@@ -1,0 +1,348 @@
+"""ctypes binding of libof_b200.so (include/of_b200.h) -- the only way the drop-in modules
+reach the GPU.  There is no CPU fallback: if the library is not built or no CUDA device is
+present, every compute call raises.
+
+Host side of the drop-in boundary: NumPy arrays in, NumPy arrays out, same argument
+meaning as the reference's functions (python/lucas_kanade_core.py,
+python/lucas_kanade_pyramidal.py).  ``*_dev`` helpers take raw device pointers (e.g.
+``torch.Tensor.data_ptr()``) for batched, device-resident use.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libof_b200.so"
+
+MODE_EXACT = 0
+MODE_FAST = 1
+FX_MIRROR_AVG_QUIRK = 1
+
+_STATUS = {
+    1: "invalid argument",
+    2: "CUDA error",
+    3: "unsupported",
+    4: "no CUDA device",
+    5: "out of device memory",
+}
+
+
+class OFBackendError(RuntimeError):
+    """The CUDA backend failed (or is missing).  Never silently replaced by CPU code."""
+
+
+_lib = None
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_i16p = C.POINTER(C.c_int16)
+_i32p = C.POINTER(C.c_int)
+_vp = C.c_void_p
+_i = C.c_int
+
+# name -> (restype, argtypes); also the list the ABI test checks against include/of_b200.h
+SIGNATURES = {
+    "of_version": (_i, []),
+    "of_last_error": (C.c_char_p, []),
+    "of_device_count": (_i, []),
+    "of_set_device": (_i, [_i]),
+    "of_kernel_launches": (C.c_longlong, []),
+    "of_host_alloc_pinned": (_i, [C.POINTER(_vp), C.c_size_t]),
+    "of_host_free_pinned": (_i, [_vp]),
+    "of_gradients_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "of_lk_from_gradients_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "of_lk_single_scale_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
+    "of_pyramid_down_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i]),
+    "of_warp_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
+    "of_upsample_flow_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "of_lk_pyramidal_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "of_lk_single_scale_fx": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "of_lk_single_scale_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "of_lk_pyramidal_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
+    "of_lk_pyramidal_f32_dev": (
+        _i,
+        [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, C.c_size_t, _vp, _vp, _vp],
+    ),
+    "of_lk_single_scale_fx_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libof_b200.so once.  Raises OFBackendError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise OFBackendError(
+                f"{LIB_PATH} is missing: build it with `python optical-flow-fpga_b200/build.py` "
+                "(nvcc, sm_100a).  This backend has no CPU fallback."
+            )
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        msg = lib().of_last_error().decode("utf-8", "replace")
+        kind = _STATUS.get(status, f"status {status}")
+        if status == 1:
+            raise ValueError(f"of_b200: {msg}")
+        raise OFBackendError(f"of_b200 {kind}: {msg}")
+
+
+def device_count() -> int:
+    return int(lib().of_device_count())
+
+
+def set_device(ordinal: int) -> None:
+    _check(lib().of_set_device(int(ordinal)))
+
+
+def kernel_launches() -> int:
+    return int(lib().of_kernel_launches())
+
+
+def default_mode() -> int:
+    """EXACT unless OF_B200_MODE=fast: parity with the reference comes first."""
+    return MODE_FAST if os.environ.get("OF_B200_MODE", "exact").lower() == "fast" else MODE_EXACT
+
+
+def _frame(a, name: str) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.float32)
+    if arr.ndim != 2:
+        raise ValueError(f"{name} must be a 2-D array, got shape {arr.shape}")
+    return arr
+
+
+def _same_shape(*arrs: np.ndarray) -> None:
+    s = arrs[0].shape
+    for a in arrs[1:]:
+        if a.shape != s:
+            raise ValueError(f"shape mismatch: {s} vs {a.shape}")
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def _window(window_size: int) -> int:
+    w = int(window_size)
+    if w < 1 or w % 2 == 0:
+        raise ValueError("window_size must be odd")
+    return w
+
+
+def gaussian_weights(sigma: float, truncate: float = 4.0) -> np.ndarray:
+    """The float64 taps scipy.ndimage.gaussian_filter uses for this sigma, built with the
+    same NumPy expression so the kernel multiplies by bit-identical weights."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (float(sigma) * float(sigma)) * x**2)
+    return np.ascontiguousarray(phi / phi.sum(), dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------
+# host-array API (NumPy in / NumPy out)
+# --------------------------------------------------------------------------------------
+def gradients(frame_prev, frame_curr):
+    p, c = _frame(frame_prev, "frame_prev"), _frame(frame_curr, "frame_curr")
+    _same_shape(p, c)
+    h, w = p.shape
+    ix, iy, it = (np.empty((h, w), np.float32) for _ in range(3))
+    _check(lib().of_gradients_f32(_ptr(p), _ptr(c), _ptr(ix), _ptr(iy), _ptr(it), h, w))
+    return ix, iy, it
+
+
+def lk_from_gradients(ix, iy, it, window_size: int = 5):
+    gx, gy, gt = _frame(ix, "Ix"), _frame(iy, "Iy"), _frame(it, "It")
+    _same_shape(gx, gy, gt)
+    h, w = gx.shape
+    u, v = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+    _check(lib().of_lk_from_gradients_f32(_ptr(gx), _ptr(gy), _ptr(gt), _ptr(u), _ptr(v), h, w, _window(window_size)))
+    return u, v
+
+
+def lk_single_scale(frame_prev, frame_curr, window_size: int = 5, mode: Optional[int] = None):
+    p, c = _frame(frame_prev, "frame_prev"), _frame(frame_curr, "frame_curr")
+    _same_shape(p, c)
+    h, w = p.shape
+    u, v = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+    m = default_mode() if mode is None else int(mode)
+    _check(lib().of_lk_single_scale_f32(_ptr(p), _ptr(c), _ptr(u), _ptr(v), 1, h, w, _window(window_size), m))
+    return u, v
+
+
+def lk_single_scale_batch(prev, curr, window_size: int = 5, mode: Optional[int] = None, out=None):
+    """[B, H, W] float32 stacks of independent frame pairs -> (u, v) stacks."""
+    p = np.ascontiguousarray(prev, dtype=np.float32)
+    c = np.ascontiguousarray(curr, dtype=np.float32)
+    if p.ndim != 3 or p.shape != c.shape:
+        raise ValueError("prev and curr must be [B, H, W] arrays of equal shape")
+    b, h, w = p.shape
+    if out is None:
+        u, v = np.empty_like(p), np.empty_like(p)
+    else:
+        u, v = out
+    m = default_mode() if mode is None else int(mode)
+    _check(lib().of_lk_single_scale_f32(_ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, _window(window_size), m))
+    return u, v
+
+
+def pyramid_down(image, scale_factor: float = 0.5):
+    """One coarser level: gaussian_filter(sigma = 1/scale_factor) + bilinear decimation."""
+    src = _frame(image, "image")
+    h, w = src.shape
+    oh, ow = int(h * scale_factor), int(w * scale_factor)
+    if oh < 1 or ow < 1:
+        raise ValueError("image too small to downsample")
+    wts = gaussian_weights(1.0 / scale_factor)
+    dst = np.empty((oh, ow), np.float32)
+    _check(lib().of_pyramid_down_f32(_ptr(src), _ptr(dst), h, w, oh, ow, _ptr(wts), (len(wts) - 1) // 2))
+    return dst
+
+
+def warp(image, flow_u, flow_v):
+    img, fu, fv = _frame(image, "image"), _frame(flow_u, "flow_u"), _frame(flow_v, "flow_v")
+    _same_shape(img, fu, fv)
+    h, w = img.shape
+    out = np.empty((h, w), np.float32)
+    _check(lib().of_warp_f32(_ptr(img), _ptr(fu), _ptr(fv), _ptr(out), h, w))
+    return out
+
+
+def upsample_flow(flow_u, flow_v, target_shape: Tuple[int, int]):
+    cu, cv = _frame(flow_u, "flow_u"), _frame(flow_v, "flow_v")
+    _same_shape(cu, cv)
+    ch, cw = cu.shape
+    th, tw = int(target_shape[0]), int(target_shape[1])
+    u, v = np.empty((th, tw), np.float32), np.empty((th, tw), np.float32)
+    _check(lib().of_upsample_flow_f32(_ptr(cu), _ptr(cv), _ptr(u), _ptr(v), ch, cw, th, tw))
+    return u, v
+
+
+def lk_pyramidal_batch(
+    prev,
+    curr,
+    num_levels: int = 3,
+    window_size: int = 5,
+    num_iterations: int = 3,
+    mode: Optional[int] = None,
+    scale_factor: float = 0.5,
+    return_trace: bool = False,
+):
+    """[B, H, W] stacks -> (u, v) stacks; optional trace = (iters_executed [B, L],
+    residuals [B, L, I, 2]) with level 0 = coarsest, like the reference's loop index."""
+    p = np.ascontiguousarray(prev, dtype=np.float32)
+    c = np.ascontiguousarray(curr, dtype=np.float32)
+    if p.ndim != 3 or p.shape != c.shape:
+        raise ValueError("prev and curr must be [B, H, W] arrays of equal shape")
+    if scale_factor != 0.5:
+        raise ValueError("only scale_factor = 0.5 (the reference's value) is supported")
+    b, h, w = p.shape
+    levels, iters = int(num_levels), int(num_iterations)
+    u, v = np.empty_like(p), np.empty_like(p)
+    wts = gaussian_weights(1.0 / scale_factor)
+    it_exec = np.zeros((b, max(levels, 1)), np.int32)
+    resid = np.zeros((b, max(levels, 1), max(iters, 1), 2), np.float32)
+    m = default_mode() if mode is None else int(mode)
+    _check(
+        lib().of_lk_pyramidal_f32(
+            _ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, levels, _window(window_size), iters, m,
+            _ptr(wts), (len(wts) - 1) // 2, _ptr(it_exec), _ptr(resid),
+        )
+    )
+    if return_trace:
+        return u, v, (it_exec, resid)
+    return u, v
+
+
+def lk_pyramidal(frame_prev, frame_curr, num_levels=3, window_size=5, num_iterations=3, mode=None, return_trace=False):
+    p, c = _frame(frame_prev, "frame_prev"), _frame(frame_curr, "frame_curr")
+    _same_shape(p, c)
+    res = lk_pyramidal_batch(p[None], c[None], num_levels, window_size, num_iterations, mode, 0.5, return_trace)
+    if return_trace:
+        return res[0][0], res[1][0], (res[2][0][0], res[2][1][0])
+    return res[0][0], res[1][0]
+
+
+def lk_single_scale_fx(prev_u8, curr_u8, mirror_avg_quirk: bool = True):
+    """uint8 frame pair(s) -> int16 S8.7 flow (value / 128 = pixels), RTL integer datapath."""
+    p = np.ascontiguousarray(prev_u8, dtype=np.uint8)
+    c = np.ascontiguousarray(curr_u8, dtype=np.uint8)
+    if p.shape != c.shape or p.ndim not in (2, 3):
+        raise ValueError("prev and curr must be uint8 arrays of equal shape, [H, W] or [B, H, W]")
+    b = 1 if p.ndim == 2 else p.shape[0]
+    h, w = p.shape[-2:]
+    u, v = np.empty(p.shape, np.int16), np.empty(p.shape, np.int16)
+    flags = FX_MIRROR_AVG_QUIRK if mirror_avg_quirk else 0
+    _check(lib().of_lk_single_scale_fx(_ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, flags))
+    return u, v
+
+
+# --------------------------------------------------------------------------------------
+# pinned host memory and device-pointer API
+# --------------------------------------------------------------------------------------
+class PinnedArray:
+    """A NumPy array whose storage is page-locked host memory (cudaHostAlloc), so the
+    library's chunked H2D / D2H copies overlap with its kernels."""
+
+    def __init__(self, shape: Sequence[int], dtype=np.float32):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(lib().of_host_alloc_pinned(C.byref(p), self.nbytes))
+        self._ptr = p
+        buf = (C.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self) -> None:
+        if self._ptr is not None:
+            self.array = None
+            lib().of_host_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def lk_single_scale_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, window_size=5, mode=MODE_FAST, stream=0):
+    _check(
+        lib().of_lk_single_scale_f32_dev(
+            prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, _window(window_size), mode, stream
+        )
+    )
+
+
+def lk_pyramidal_workspace_bytes(batch, height, width, levels, iterations) -> int:
+    return int(lib().of_lk_pyramidal_workspace_bytes(batch, height, width, levels, iterations))
+
+
+def lk_pyramidal_dev(
+    prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, levels, window_size, iterations, mode,
+    workspace_ptr, workspace_bytes, iters_ptr=None, resid_ptr=None, stream=0, weights: Optional[np.ndarray] = None,
+):
+    wts = gaussian_weights(2.0) if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    _check(
+        lib().of_lk_pyramidal_f32_dev(
+            prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, levels, _window(window_size), iterations, mode,
+            _ptr(wts), (len(wts) - 1) // 2, workspace_ptr, workspace_bytes, iters_ptr, resid_ptr, stream,
+        )
+    )
+
+
+def lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, mirror_avg_quirk=True, stream=0):
+    flags = FX_MIRROR_AVG_QUIRK if mirror_avg_quirk else 0
+    _check(lib().of_lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, flags, stream))

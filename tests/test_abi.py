@@ -1,0 +1,140 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/of_b200.h declares, the ctypes table covers them, the drop-in modules keep the
+reference's signatures, and nothing falls back to CPU arithmetic when no GPU is present."""
+
+import inspect
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import BACKEND_DIR, ROOT
+
+
+@pytest.fixture(scope="module")
+def of_b200():
+    sys.path.insert(0, str(BACKEND_DIR))
+    import build as of_build  # optical-flow-fpga_b200/build.py
+
+    of_build.build()
+    import of_b200 as mod
+
+    return mod
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "of_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(of_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(of_b200):
+    names = declared_symbols()
+    assert len(names) >= 19
+    lib = of_b200.lib()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/of_b200.h but not exported"
+    assert sorted(of_b200.SIGNATURES) == names
+    out = subprocess.run(["nm", "-D", "--defined-only", str(of_b200.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\sT\s+(of_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+
+
+def test_version_and_error_string(of_b200):
+    assert of_b200.lib().of_version() == 100
+    assert isinstance(of_b200.lib().of_last_error(), bytes)
+
+
+def test_library_contains_sm100a_tma_code(of_b200):
+    sass = subprocess.run(["cuobjdump", "-sass", str(of_b200.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTMALDG" in sass, "the fast kernel must stage frames with TMA"
+
+
+def test_argument_errors_come_before_any_device_work(of_b200):
+    z = np.zeros((16, 16), np.float32)
+    with pytest.raises(ValueError):
+        of_b200.lk_single_scale(z, z, window_size=4)
+    with pytest.raises(ValueError):
+        of_b200.lk_single_scale(z, np.zeros((16, 20), np.float32))
+    with pytest.raises(ValueError):
+        of_b200.lk_single_scale(np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4), np.float32))
+
+
+def test_no_cpu_fallback_without_a_device(of_b200):
+    if of_b200.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    z = np.zeros((16, 16), np.float32)
+    with pytest.raises(of_b200.OFBackendError):
+        of_b200.lk_single_scale(z, z)
+    with pytest.raises(of_b200.OFBackendError):
+        of_b200.lk_pyramidal(z, z)
+    with pytest.raises(of_b200.OFBackendError):
+        of_b200.lk_single_scale_fx(np.zeros((16, 16), np.uint8), np.zeros((16, 16), np.uint8))
+
+
+def test_product_never_imports_the_oracle():
+    for py in BACKEND_DIR.glob("*.py"):
+        src = py.read_text()
+        assert "oracle" not in src.replace("oracle/", ""), f"{py.name} mentions the oracle"
+    for cu in (BACKEND_DIR / "csrc").iterdir():
+        assert "oracle" not in cu.read_text()
+
+
+REFERENCE_SIGNATURES = {
+    # python/lucas_kanade_core.py:15,48,73
+    ("lucas_kanade_core", "compute_gradients"): ["frame_prev", "frame_curr"],
+    ("lucas_kanade_core", "lucas_kanade_single_scale"): ["frame_prev", "frame_curr", ("window_size", 5)],
+    ("lucas_kanade_core", "lucas_kanade_from_gradients"): ["Ix", "Iy", "It", ("window_size", 5)],
+    # python/lucas_kanade_pyramidal.py:23,66,100,141,231,313,354
+    ("lucas_kanade_pyramidal", "build_gaussian_pyramid"): ["image", "num_levels", ("scale_factor", 0.5)],
+    ("lucas_kanade_pyramidal", "warp_image"): ["image", "flow_u", "flow_v"],
+    ("lucas_kanade_pyramidal", "upsample_flow"): ["flow_u", "flow_v", "target_shape"],
+    ("lucas_kanade_pyramidal", "lucas_kanade_pyramidal"): [
+        "frame_prev", "frame_curr", ("num_levels", 3), ("window_size", 5), ("num_iterations", 3)],
+    ("lucas_kanade_pyramidal", "visualize_flow_comparison"): [
+        "flow_u_single", "flow_v_single", "flow_u_pyr", "flow_v_pyr", "output_path", ("scale", 1.0)],
+    ("lucas_kanade_pyramidal", "visualize_pyramid_level"): [
+        "flow_u", "flow_v", "level", ("num_levels", 3), ("output_dir", "python/output")],
+    ("lucas_kanade_pyramidal", "main"): [],
+    # python/lucas_kanade_reference.py:22,78,106
+    ("lucas_kanade_reference", "visualize_flow"): ["u", "v", "output_path", ("scale", 10.0)],
+    ("lucas_kanade_reference", "export_flow_field_txt"): [
+        "u", "v", "output_path", "width", "height", ("test_region", None)],
+    ("lucas_kanade_reference", "main"): [],
+}
+
+
+def test_drop_in_modules_keep_reference_signatures(of_b200):
+    import importlib
+
+    for (mod_name, fn_name), expected in REFERENCE_SIGNATURES.items():
+        mod = importlib.import_module(mod_name)
+        assert str(BACKEND_DIR) in mod.__file__
+        params = list(inspect.signature(getattr(mod, fn_name)).parameters.values())
+        got = [p.name if p.default is inspect.Parameter.empty else (p.name, p.default) for p in params]
+        assert got == expected, (mod_name, fn_name)
+    ref = importlib.import_module("lucas_kanade_reference")
+    for const in ("SCRIPT_DIR", "PROJECT_ROOT", "DEFAULT_FRAME_DIR", "DEFAULT_OUTPUT_DIR"):
+        assert hasattr(ref, const)
+
+
+def test_flow_field_text_export_format(of_b200, tmp_path):
+    import lucas_kanade_reference as ref
+
+    u = np.arange(6, dtype=np.float32).reshape(2, 3) / 4
+    v = -u
+    out = tmp_path / "flow.txt"
+    ref.export_flow_field_txt(u, v, out, width=3, height=2, test_region={"x_min": 0, "x_max": 1, "y_min": 0, "y_max": 1})
+    lines = out.read_text().splitlines()
+    assert lines[:4] == [
+        "# Optical flow field data (Python reference)",
+        "# Format: x y u v",
+        "# Image size: 3x2",
+        "# Test region: x[0:1], y[0:1]",
+    ]
+    assert lines[4] == "0 0 0.000000 -0.000000" or lines[4] == "0 0 0.000000 0.000000"
+    assert lines[-1] == "2 1 1.250000 -1.250000"
+    assert len(lines) == 4 + 6

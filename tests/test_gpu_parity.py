@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference goldens.
+
+All comparisons of the float path in EXACT mode are bit-exact.  FAST mode is bit-exact on
+uint8-valued frames (the verifier's inputs and the benchmark's synthetic frames) and is
+held to the north star's tolerance (max |du|, |dv| <= 1e-3 px, MAE/EPE equal to 3 decimals)
+where floats are not exactly summable.  The fixed-point mode is bit-exact against the
+integer oracle.
+"""
+
+import hashlib
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import BACKEND_DIR
+
+sys.path.insert(0, str(BACKEND_DIR))
+
+from oracle import flow_metrics_oracle as fm  # noqa: E402
+from oracle import lk_fixed_oracle as fxo  # noqa: E402
+from oracle import lk_float_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ofb():
+    import build as of_build
+
+    of_build.build()
+    import of_b200
+
+    assert of_b200.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return of_b200
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def assert_bit_equal(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, what
+    if a.dtype == np.float32:
+        neq = bits(a) != bits(b)
+    else:
+        neq = a != b
+    assert not neq.any(), f"{what}: {int(neq.sum())} of {a.size} values differ, first at {np.argwhere(neq)[:3].tolist()}"
+
+
+# ---------------------------------------------------------------------------------------
+# drop-in modules against the reference's golden outputs
+# ---------------------------------------------------------------------------------------
+def test_single_scale_13_patterns_bit_exact(ofb, golden_index, golden_frames):
+    import lucas_kanade_core as core
+
+    for name, entry in golden_index["patterns"].items():
+        p, c = (f.astype(np.float32) for f in golden_frames[name])
+        for mode in (ofb.MODE_EXACT, ofb.MODE_FAST):
+            u, v = ofb.lk_single_scale(p, c, 5, mode=mode)
+            assert sha(u) == entry["single_scale"]["sha256_u"], (name, mode)
+            assert sha(v) == entry["single_scale"]["sha256_v"], (name, mode)
+        u, v = core.lucas_kanade_single_scale(p, c)  # the module the verifier imports
+        assert sha(u) == entry["single_scale"]["sha256_u"]
+        assert u.dtype == np.float32 and u.flags["C_CONTIGUOUS"]
+
+
+def test_pyramidal_13_patterns_bit_exact_and_metrics(ofb, golden_index, golden_frames, capsys):
+    import lucas_kanade_pyramidal as pyr
+
+    for name, entry in golden_index["patterns"].items():
+        p, c = (f.astype(np.float32) for f in golden_frames[name])
+        u, v, (iters, resid) = ofb.lk_pyramidal(p, c, 3, 5, 3, mode=ofb.MODE_EXACT, return_trace=True)
+        assert sha(u) == entry["pyramidal"]["sha256_u"], name
+        assert sha(v) == entry["pyramidal"]["sha256_v"], name
+        ref_iters = sum(1 for ln in entry["pyramidal"]["reference_log"] if ln.startswith("Iteration"))
+        assert int(iters.sum()) == ref_iters, name
+        mask = fm.test_region_mask(p.shape, name, golden_index["center_crop"])
+        gt = entry["ground_truth"]
+        m = fm.all_metrics(u, v, gt["u"], gt["v"], mask)
+        for k, val in entry["verification_baseline"]["pyramidal"].items():
+            assert m[k] == val, (name, k)
+    u2, v2 = pyr.lucas_kanade_pyramidal(p, c, num_levels=3, window_size=5, num_iterations=3)
+    capsys.readouterr()
+    assert_bit_equal(u2, u, "drop-in module")
+    assert_bit_equal(v2, v, "drop-in module")
+
+
+def test_no_motion_converges_after_one_iteration_per_level(ofb, golden_frames):
+    p, c = (f.astype(np.float32) for f in golden_frames["no_motion"])
+    u, v, (iters, resid) = ofb.lk_pyramidal(p, c, 3, 5, 3, return_trace=True)
+    assert iters.tolist() == [1, 1, 1]
+    assert not u.any() and not v.any()
+
+
+def test_helpers_against_reference_units(ofb, golden_units):
+    import lucas_kanade_core as core
+    import lucas_kanade_pyramidal as pyr
+
+    g = golden_units
+    ix, iy, it = core.compute_gradients(g["grad_prev"], g["grad_curr"])
+    assert_bit_equal(ix, g["grad_ix"], "Ix")
+    assert_bit_equal(iy, g["grad_iy"], "Iy")
+    assert_bit_equal(it, g["grad_it"], "It")
+
+    u, v = core.lucas_kanade_from_gradients(g["fg_ix"], g["fg_iy"], g["fg_it"], 5)
+    assert_bit_equal(u, g["fg_u"], "from_gradients u")
+    assert_bit_equal(v, g["fg_v"], "from_gradients v")
+
+    levels = pyr.build_gaussian_pyramid(g["grad_prev"], 4)
+    for i, lvl in enumerate(levels):
+        assert_bit_equal(lvl, g[f"pyr4_level{i}"], f"pyramid level {i}")
+    levels = pyr.build_gaussian_pyramid(g["pyr_odd_in"], 3)
+    for i, lvl in enumerate(levels):
+        assert_bit_equal(lvl, g[f"pyr_odd_level{i}"], f"odd pyramid level {i}")
+
+    out = pyr.warp_image(g["warp_img"], g["warp_u"], g["warp_v"])
+    assert_bit_equal(out, g["warp_out"], "warp")
+    for shape in ((60, 80), (61, 83)):
+        uu, vv = pyr.upsample_flow(g["up_u"], g["up_v"], shape)
+        assert_bit_equal(uu, g[f"up_out_u_{shape[0]}x{shape[1]}"], "upsample u")
+        assert_bit_equal(vv, g[f"up_out_v_{shape[0]}x{shape[1]}"], "upsample v")
+
+
+@pytest.mark.parametrize("w", [3, 5, 7])
+def test_general_float_frames_exact_mode(ofb, golden_units, w):
+    g = golden_units
+    u, v = ofb.lk_single_scale(g[f"float_w{w}_prev"], g[f"float_w{w}_curr"], w, mode=ofb.MODE_EXACT)
+    assert_bit_equal(u, g[f"float_w{w}_u"], f"w={w} u")
+    assert_bit_equal(v, g[f"float_w{w}_v"], f"w={w} v")
+
+
+def test_small_pyramidal_window7(ofb, golden_units):
+    g = golden_units
+    u, v = ofb.lk_pyramidal(g["pyr_small_prev"], g["pyr_small_curr"], 2, 7, 2)
+    assert_bit_equal(u, g["pyr_small_u"], "u")
+    assert_bit_equal(v, g["pyr_small_v"], "v")
+
+
+# ---------------------------------------------------------------------------------------
+# CUDA path against the oracle on seeded inputs (shapes the goldens do not cover)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(7, 8), (33, 8), (52, 124), (100, 248), (64, 120), (61, 364), (240, 320)])
+def test_fast_kernel_ragged_shapes_uint8_frames(ofb, shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    # smooth-ish uint8 texture so that the window sums stay exactly representable
+    base = rng.integers(0, 256, size=(shape[0] + 8, shape[1] + 8)).astype(np.float32)
+    k = np.ones((5, 5), np.float32) / 25
+    from scipy.signal import convolve2d
+
+    sm = np.rint(convolve2d(base, k, mode="same")).astype(np.float32)
+    p = sm[4:-4, 4:-4].copy()
+    c = sm[3:-5, 5:-3].copy()
+    uo, vo = orc.lucas_kanade_single_scale(p, c, 5)
+    for mode in (ofb.MODE_FAST, ofb.MODE_EXACT):
+        u, v = ofb.lk_single_scale(p, c, 5, mode=mode)
+        assert_bit_equal(u, uo, f"{shape} mode {mode} u")
+        assert_bit_equal(v, vo, f"{shape} mode {mode} v")
+
+
+@pytest.mark.parametrize("w", [1, 3, 5, 7, 9, 11])
+def test_exact_mode_all_windows_random_floats(ofb, w):
+    rng = np.random.default_rng(w)
+    p = (rng.random((41, 67)) * 255).astype(np.float32)
+    c = (p + rng.standard_normal((41, 67)).astype(np.float32) * 3).astype(np.float32)
+    uo, vo = orc.lucas_kanade_single_scale(p, c, w)
+    u, v = ofb.lk_single_scale(p, c, w, mode=ofb.MODE_EXACT)
+    assert_bit_equal(u, uo, f"w={w} u")
+    assert_bit_equal(v, vo, f"w={w} v")
+
+
+def test_fast_mode_on_general_floats_is_within_tolerance(ofb):
+    """Not exactly summable inputs: FAST differs from the reference order only by rounding."""
+    rng = np.random.default_rng(5)
+    from scipy.ndimage import gaussian_filter
+
+    p = gaussian_filter((rng.random((120, 240)) * 255).astype(np.float32), 1.5)
+    c = np.roll(p, 1, axis=1) + rng.standard_normal(p.shape).astype(np.float32) * 0.01
+    c = c.astype(np.float32)
+    uo, vo = orc.lucas_kanade_single_scale(p, c, 5)
+    u, v = ofb.lk_single_scale(p, c, 5, mode=ofb.MODE_FAST)
+    # well-conditioned pixels only: |det| >> eps, where 1e-3 px is meaningful
+    ix, iy, it = orc.compute_gradients(p, c)
+    sxx, syy, sxy, _, _ = orc.window_sums(ix, iy, it, 5)
+    det = np.zeros_like(p)
+    det[2:-2, 2:-2] = sxx * syy - sxy * sxy
+    good = det > 1.0
+    assert good.mean() > 0.5
+    assert np.max(np.abs(u - uo)[good]) <= 1e-3
+    assert np.max(np.abs(v - vo)[good]) <= 1e-3
+
+
+def test_batch_equals_single_pairs_and_is_deterministic(ofb):
+    import synthetic
+
+    prev, curr, _ = synthetic.make_pairs_numpy(5, 96, 248, seed=3)
+    for mode in (ofb.MODE_FAST, ofb.MODE_EXACT):
+        ub, vb = ofb.lk_single_scale_batch(prev, curr, 5, mode=mode)
+        ub2, vb2 = ofb.lk_single_scale_batch(prev, curr, 5, mode=mode)
+        assert_bit_equal(ub, ub2, "determinism")
+        for b in range(5):
+            u, v = ofb.lk_single_scale(prev[b], curr[b], 5, mode=mode)
+            assert_bit_equal(ub[b], u, f"pair {b}")
+            assert_bit_equal(vb[b], v, f"pair {b}")
+    uo, vo = orc.lucas_kanade_single_scale(prev[4], curr[4], 5)
+    assert_bit_equal(ub[4], uo, "oracle")
+    assert_bit_equal(vb[4], vo, "oracle")
+
+
+def test_pyramidal_batch_with_mixed_convergence(ofb, golden_frames):
+    """Pairs of one batch stop iterating independently (no_motion exits early, the others do not)."""
+    names = ["translate_small", "no_motion", "rotate_small"]
+    prev = np.stack([golden_frames[n][0] for n in names]).astype(np.float32)
+    curr = np.stack([golden_frames[n][1] for n in names]).astype(np.float32)
+    u, v, (iters, resid) = ofb.lk_pyramidal_batch(prev, curr, 3, 5, 3, return_trace=True)
+    assert iters[1].tolist() == [1, 1, 1] and iters[0].tolist() == [3, 3, 3]
+    for b, n in enumerate(names):
+        uo, vo = orc.lucas_kanade_pyramidal(prev[b], curr[b], 3, 5, 3)
+        assert_bit_equal(u[b], uo, n)
+        assert_bit_equal(v[b], vo, n)
+
+
+@pytest.mark.parametrize("levels,iters,shape", [(1, 2, (40, 56)), (2, 1, (45, 67)), (4, 2, (128, 160)), (3, 0, (64, 64))])
+def test_pyramidal_other_presets_against_oracle(ofb, levels, iters, shape):
+    rng = np.random.default_rng(levels * 10 + iters)
+    from scipy.ndimage import gaussian_filter, shift
+
+    p = gaussian_filter((rng.random(shape) * 255).astype(np.float32), 1.0)
+    c = shift(p, (0.7, -1.3), order=1, mode="nearest").astype(np.float32)
+    uo, vo = orc.lucas_kanade_pyramidal(p, c, levels, 5, iters)
+    u, v = ofb.lk_pyramidal(p, c, levels, 5, iters)
+    assert_bit_equal(u, uo, "u")
+    assert_bit_equal(v, vo, "v")
+
+
+# ---------------------------------------------------------------------------------------
+# full-size frames: oracle on one pair + size-independent properties
+# ---------------------------------------------------------------------------------------
+def test_1080p_batch_against_oracle_and_locality(ofb):
+    import synthetic
+
+    prev, curr, _ = synthetic.make_pairs_numpy(3, 1080, 1920, seed=11)
+    u, v = ofb.lk_single_scale_batch(prev, curr, 5, mode=ofb.MODE_FAST)
+    uo, vo = orc.lucas_kanade_single_scale(prev[1], curr[1], 5)
+    assert_bit_equal(u[1], uo, "1080p u")
+    assert_bit_equal(v[1], vo, "1080p v")
+    # locality: flow at a pixel depends on a 7x7 neighbourhood only, so a crop computed on
+    # its own agrees with the full frame 3 pixels inside the crop
+    ys, xs = slice(401, 701), slice(1000, 1400)
+    uc, vc = ofb.lk_single_scale(prev[2][ys, xs], curr[2][ys, xs], 5, mode=ofb.MODE_FAST)
+    assert_bit_equal(uc[3:-3, 3:-3], u[2][ys, xs][3:-3, 3:-3], "crop u")
+    assert_bit_equal(vc[3:-3, 3:-3], v[2][ys, xs][3:-3, 3:-3], "crop v")
+    # identical frames -> exactly zero flow; the window_size // 2 border is zero
+    uz, vz = ofb.lk_single_scale(prev[0], prev[0], 5, mode=ofb.MODE_FAST)
+    assert not uz.any() and not vz.any()
+    for arr in (u, v):
+        assert not arr[:, :2].any() and not arr[:, -2:].any() and not arr[:, :, :2].any() and not arr[:, :, -2:].any()
+
+
+def test_4k_fast_equals_exact_kernel(ofb):
+    import synthetic
+
+    prev, curr, _ = synthetic.make_pairs_numpy(1, 2160, 3840, seed=12)
+    uf, vf = ofb.lk_single_scale(prev[0], curr[0], 5, mode=ofb.MODE_FAST)
+    ue, ve = ofb.lk_single_scale(prev[0], curr[0], 5, mode=ofb.MODE_EXACT)
+    assert_bit_equal(uf, ue, "4K u")
+    assert_bit_equal(vf, ve, "4K v")
+
+
+# ---------------------------------------------------------------------------------------
+# fixed-point (RTL) mode
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("quirk", [True, False])
+def test_fixed_point_mode_bit_exact(ofb, golden_frames, quirk):
+    for name in ("translate_medium", "rotate_large", "no_motion"):
+        p, c = golden_frames[name]
+        uo, vo = fxo.lk_single_scale_fx(p, c, mirror_avg_quirk=quirk)
+        u, v = ofb.lk_single_scale_fx(p, c, mirror_avg_quirk=quirk)
+        assert u.dtype == np.int16
+        assert_bit_equal(u, uo, f"{name} u")
+        assert_bit_equal(v, vo, f"{name} v")
+    rng = np.random.default_rng(9)
+    p = rng.integers(0, 256, size=(3, 37, 75), dtype=np.uint8)  # worst-case contrast: exercises the 32-bit wraps
+    c = rng.integers(0, 256, size=(3, 37, 75), dtype=np.uint8)
+    u, v = ofb.lk_single_scale_fx(p, c, mirror_avg_quirk=quirk)
+    for b in range(3):
+        uo, vo = fxo.lk_single_scale_fx(p[b], c[b], mirror_avg_quirk=quirk)
+        assert_bit_equal(u[b], uo, f"random {b} u")
+        assert_bit_equal(v[b], vo, f"random {b} v")
+    assert np.abs(u).max() <= 1024 and np.abs(v).max() <= 1024
+
+
+def test_error_behaviour(ofb):
+    z = np.zeros((16, 16), np.float32)
+    with pytest.raises(ValueError):
+        ofb.lk_single_scale(z, z, window_size=6)
+    with pytest.raises(ofb.OFBackendError):
+        ofb.lk_single_scale(z, z, window_size=13)  # unsupported, not silently approximated
+    with pytest.raises(ValueError):
+        ofb.lk_pyramidal(z, z, num_levels=6)  # 16 -> 8 -> 4 -> 2 -> 1 -> 0
+    u, v = ofb.lk_single_scale(np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32), 5)
+    assert u.shape == (3, 3) and not u.any()  # smaller than the window: all border
