@@ -325,19 +325,29 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
 
         idx = [0, B // 2, B - 1] if not wl["pyramidal"] else [0]
         ok = True
+        worst, frac_big, mean_diff = 0.0, 0.0, 0.0
         for b in idx:
             p_h, c_h = prev[b].cpu().numpy(), curr[b].cpu().numpy()
             if wl["pyramidal"]:
                 uo, vo = orc.lucas_kanade_pyramidal(p_h, c_h, wl["levels"], WINDOW, wl["iters"])
             else:
                 uo, vo = orc.lucas_kanade_single_scale(p_h, c_h, WINDOW)
-            ok &= bool(np.array_equal(u[b].cpu().numpy().view(np.uint32), uo.view(np.uint32)))
-            ok &= bool(np.array_equal(v[b].cpu().numpy().view(np.uint32), vo.view(np.uint32)))
-        parity = {"bit_exact_vs_oracle": ok, "pairs_checked": len(idx)}
+            ug, vg = u[b].cpu().numpy(), v[b].cpu().numpy()
+            ok &= bool(np.array_equal(ug.view(np.uint32), uo.view(np.uint32)))
+            ok &= bool(np.array_equal(vg.view(np.uint32), vo.view(np.uint32)))
+            d = np.maximum(np.abs(ug - uo), np.abs(vg - vo))
+            worst = max(worst, float(d.max()))
+            frac_big = max(frac_big, float((d > 1e-3).mean()))
+            mean_diff = max(mean_diff, float(d.mean()))
+        parity = {"bit_exact_vs_oracle": ok, "pairs_checked": len(idx), "max_abs_diff_px": worst,
+                  "frac_pixels_diff_gt_1e-3": frac_big, "mean_abs_diff_px": mean_diff}
+        if wl["pyramidal"]:
+            parity["note"] = ("fast mode: warp is the reference's float64 bilinear bit for bit, window sums are "
+                              "separable float32 (different association), so ill-conditioned pixels can move")
 
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
     e2e = None
-    if not wl["pyramidal"]:
+    if not wl["pyramidal"] and not args.no_e2e:
         hp = of_b200.PinnedArray((B, H, W))
         hc = of_b200.PinnedArray((B, H, W))
         hu = of_b200.PinnedArray((B, H, W))
@@ -444,6 +454,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="single_1080p")
     ap.add_argument("--batch", type=int, default=None, help="override frame pairs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (experiments)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:

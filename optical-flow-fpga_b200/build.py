@@ -13,7 +13,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB = HERE / "libof_b200.so"
+LIB = HERE / os.environ.get("OF_B200_LIB_NAME", "libof_b200.so")  # variants: experiments only
 SOURCES = ["of_api.cu", "lk_march.cu", "lk_tile.cu", "pyramid.cu", "lk_fixed.cu"]
 HEADERS = ["of_common.cuh", "of_kernels.h", "../../include/of_b200.h"]
 
@@ -44,7 +44,7 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and up_to_date():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *os.environ.get("OF_NVCC_DEFS", "").split()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]

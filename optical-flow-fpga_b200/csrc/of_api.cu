@@ -193,7 +193,7 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
 int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int levels,
                   int window, int iterations, int mode, const double* gw, int radius, void* workspace, size_t ws_bytes,
                   int* iters_dev, float* resid_dev, cudaStream_t stream, Counter& cnt) {
-    (void)mode;  // both modes run the reference-order kernels on this path for now
+    if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
     if (iterations < 0) return fail(OF_ERR_INVALID_ARGUMENT, "num_iterations must be >= 0");
     if (batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "at most 65535 pairs per call on the device entry point");
     if (levels > 1 && (!gw || radius < 0 || radius > OF_MAX_GAUSS_RADIUS))
@@ -242,24 +242,45 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                                          sel + (size_t)(k + 1) * batch, flowA_u(k), flowA_v(k), batch, p.h[k + 1],
                                          p.w[k + 1], p.h[k], p.w[k], &cnt.n, stream));
         }
+        // fast mode: the register-marching kernel where the level allows TMA (width % 4 == 0,
+        // window 5); otherwise, and always in exact mode, the reference-order tile kernel
+        RefineArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.prev = lp[k];
+        ra.curr = lc[k];
+        ra.flow_u[0] = flowA_u(k);
+        ra.flow_v[0] = flowA_v(k);
+        ra.flow_u[1] = F(p.bu_off[k]);
+        ra.flow_v[1] = F(p.bv_off[k]);
+        ra.sel = sel_k;
+        ra.done = done_k;
+        ra.partial = partial;
+        ra.H = p.h[k];
+        ra.W = p.w[k];
+        const bool fast_level = (mode == OF_MODE_FAST) && lk_refine_supported(ra, window);
         for (int it = 0; it < iterations; ++it) {
-            TileArgs a;
-            memset(&a, 0, sizeof(a));
-            a.in0 = lp[k];
-            a.in1 = lc[k];
-            a.flow_u[0] = flowA_u(k);
-            a.flow_v[0] = flowA_v(k);
-            a.flow_u[1] = F(p.bu_off[k]);
-            a.flow_v[1] = F(p.bv_off[k]);
-            a.sel = sel_k;
-            a.done = done_k;
-            a.partial = partial;
-            a.H = p.h[k];
-            a.W = p.w[k];
-            OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
+            if (fast_level) {
+                OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, stream));
+            } else {
+                TileArgs a;
+                memset(&a, 0, sizeof(a));
+                a.in0 = lp[k];
+                a.in1 = lc[k];
+                a.flow_u[0] = flowA_u(k);
+                a.flow_v[0] = flowA_v(k);
+                a.flow_u[1] = F(p.bu_off[k]);
+                a.flow_v[1] = F(p.bv_off[k]);
+                a.sel = sel_k;
+                a.done = done_k;
+                a.partial = partial;
+                a.H = p.h[k];
+                a.W = p.w[k];
+                OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
+            }
             IterFinalizeArgs f;
             f.partial = partial;
-            f.blocks_per_pair = lk_tile_blocks_per_pair(p.h[k], p.w[k]);
+            f.blocks_per_pair = fast_level ? lk_refine_units_per_pair(batch, p.h[k], p.w[k])
+                                           : lk_tile_blocks_per_pair(p.h[k], p.w[k]);
             f.H = p.h[k];
             f.W = p.w[k];
             f.sel = sel_k;

@@ -21,6 +21,23 @@ bool lk_march_supported(int H, int W, int window);
 cudaError_t launch_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W,
                             int force_path, int* launches, cudaStream_t stream);
 
+// ---- K3 fast: warp-marching refinement iteration (lk_march.cu) --------------------------
+struct RefineArgs {
+    const float* prev;  // level image of the previous frame   [B][H][W]
+    const float* curr;  // level image of the current frame (gathered through the flow)
+    float* flow_u[2];   // ping-pong flow buffers, sel[pair] = index of the current one
+    float* flow_v[2];
+    const int* sel;
+    const int* done;
+    double* partial;    // [pair][units_per_pair][2]
+    int H, W;
+    int n_strips, n_bands, band_rows;  // filled by the launcher
+    long long n_units;
+};
+bool lk_refine_supported(const RefineArgs& a, int window);
+int lk_refine_units_per_pair(int batch, int H, int W);
+cudaError_t launch_lk_refine(const RefineArgs& a, int batch, int* launches, cudaStream_t stream);
+
 // ---- K1/K3 exact: tile kernel in the reference's operation order (lk_tile.cu) ----------
 enum TileSource { SRC_FRAMES = 0, SRC_WARP = 1, SRC_GRADS = 2 };
 struct TileArgs {

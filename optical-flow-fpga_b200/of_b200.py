@@ -18,7 +18,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libof_b200.so"
+LIB_PATH = HERE / os.environ.get("OF_B200_LIB_NAME", "libof_b200.so")  # variants: experiments only
 
 MODE_EXACT = 0
 MODE_FAST = 1

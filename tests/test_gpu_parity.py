@@ -91,6 +91,47 @@ def test_pyramidal_13_patterns_bit_exact_and_metrics(ofb, golden_index, golden_f
     assert_bit_equal(v2, v, "drop-in module")
 
 
+def test_pyramidal_fast_mode_13_patterns_within_tolerance(ofb, golden_index, golden_frames):
+    """FAST pyramidal (register-marching refinement kernel): the warp is exact, the window sums
+    are separable float32.  Contract: MAE / EPE equal to the reference's to 3 decimals on every
+    verifier pattern; per-pixel deviations are confined to ill-conditioned pixels."""
+    report = {}
+    for name, entry in golden_index["patterns"].items():
+        p, c = (f.astype(np.float32) for f in golden_frames[name])
+        ue, ve = ofb.lk_pyramidal(p, c, 3, 5, 3, mode=ofb.MODE_EXACT)
+        uf, vf, (iters, _) = ofb.lk_pyramidal(p, c, 3, 5, 3, mode=ofb.MODE_FAST, return_trace=True)
+        ref_iters = sum(1 for ln in entry["pyramidal"]["reference_log"] if ln.startswith("Iteration"))
+        assert int(iters.sum()) == ref_iters, name  # same early-exit decisions
+        mask = fm.test_region_mask(p.shape, name, golden_index["center_crop"])
+        gt = entry["ground_truth"]
+        m = fm.all_metrics(uf, vf, gt["u"], gt["v"], mask)
+        for k in ("mae_u", "mae_v", "epe"):
+            assert abs(m[k] - entry["verification_baseline"]["pyramidal"][k]) < 5e-4, (name, k, m[k])
+        d = np.maximum(np.abs(uf - ue), np.abs(vf - ve))
+        report[name] = (float(d.max()), int((d > 1e-3).sum()))
+        assert (d > 1e-3).mean() < 0.05, (name, report[name])
+    print("fast-vs-exact pyramidal: max |d| px, pixels > 1e-3:", report)
+    assert report["no_motion"] == (0.0, 0)
+
+
+def test_pyramidal_fast_mode_mixed_levels(ofb):
+    """4 levels where the coarsest widths are not multiples of 4: the driver mixes the marching
+    kernel (fine levels) with the tile kernel (coarse levels) in one run."""
+    rng = np.random.default_rng(3)
+    from scipy.ndimage import gaussian_filter, shift
+
+    p = gaussian_filter((rng.random((200, 328)) * 255).astype(np.float32), 1.2)  # 328, 164, 82, 41
+    c = shift(p, (1.4, -2.2), order=1, mode="nearest").astype(np.float32)
+    ue, ve = ofb.lk_pyramidal(p, c, 4, 5, 2, mode=ofb.MODE_EXACT)
+    uo, vo = orc.lucas_kanade_pyramidal(p, c, 4, 5, 2)
+    assert_bit_equal(ue, uo, "exact u")
+    uf, vf = ofb.lk_pyramidal(p, c, 4, 5, 2, mode=ofb.MODE_FAST)
+    d = np.maximum(np.abs(uf - ue), np.abs(vf - ve))
+    assert np.median(d) < 1e-5 and (d > 1e-3).mean() < 0.05
+    uf2, vf2 = ofb.lk_pyramidal(p, c, 4, 5, 2, mode=ofb.MODE_FAST)
+    assert_bit_equal(uf, uf2, "determinism")
+
+
 def test_no_motion_converges_after_one_iteration_per_level(ofb, golden_frames):
     p, c = (f.astype(np.float32) for f in golden_frames["no_motion"])
     u, v, (iters, resid) = ofb.lk_pyramidal(p, c, 3, 5, 3, return_trace=True)
