@@ -22,6 +22,8 @@ template <int MODE>
 __global__ void k(float* out, float seed) {
     float a[CHAINS];
     unsigned long long p[CHAINS];
+    double dd[CHAINS];
+    for (int i = 0; i < CHAINS; ++i) dd[i] = seed + threadIdx.x + i;
     for (int i = 0; i < CHAINS; ++i) {
         a[i] = seed + threadIdx.x + i;
         float2 t = make_float2(a[i], a[i] + 0.5f);
@@ -39,12 +41,16 @@ __global__ void k(float* out, float seed) {
             if (MODE == 4) a[i] = __shfl_down_sync(0xffffffffu, a[i], 1);
             if (MODE == 5) a[i] = __fdiv_rn(seed, a[i]);
             if (MODE == 6) a[i] = __fmul_rn(a[i], seed);
+            if (MODE == 7) dd[i] = __dadd_rn(dd[i], (double)seed);
+            if (MODE == 8) dd[i] = __dmul_rn(dd[i], (double)seed);
+            if (MODE == 9) dd[i] = __fma_rn(dd[i], (double)seed, (double)seed);
+            if (MODE == 10) dd[i] = (double)(float)dd[i] + 1.0;
         }
     }
     float s = 0;
     for (int i = 0; i < CHAINS; ++i) {
         float2 t = *reinterpret_cast<float2*>(&p[i]);
-        s += a[i] + t.x + t.y;
+        s += a[i] + t.x + t.y + (float)dd[i];
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
@@ -79,5 +85,9 @@ int main() {
     run<6>("FMUL", 1);
     run<4>("SHFL", 1);
     run<5>("FDIV.rn", 1);
+    run<7>("DADD", 1);
+    run<8>("DMUL", 1);
+    run<9>("DFMA", 1);
+    run<10>("F2F+DADD", 1);
     return 0;
 }
