@@ -54,6 +54,21 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes(workload: str, batch: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/), only when it was taken on this exact workload; else None."""
+    f = ROOT / "profiles" / "r01_lk_march_ncu_full_summary.json"
+    if workload != "single_1080p" or batch != 256 or not f.exists():
+        return None
+    try:
+        d = json.load(open(f))
+        rd = float(d["dram__bytes_read.sum"]["values"][0]) * 1e9
+        wr = float(d["dram__bytes_write.sum"]["values"][0]) * 1e9
+        return rd + wr
+    except Exception:
+        return None
+
+
 def pyramidal_bytes_per_pixel(levels: int, iters: int) -> float:
     """Stage-fused traffic model of SURVEY.md 8(d): pyramid 2 frames x (N_{l-1}+N_l) x 4 B,
     24 B per executed iteration and level pixel, 8 B per upsampled pixel."""
@@ -68,7 +83,7 @@ def pyramidal_bytes_per_pixel(levels: int, iters: int) -> float:
 # clocks during the timed region (NVML, sampled from a thread)
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.003):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -429,7 +444,10 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": None,
+            "traffic": ncu_traffic_bytes(args.workload, B),
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
+            "profiles/r01_lk_march_ncu_full_summary.json" if ncu_traffic_bytes(args.workload, B) else None,
+            "algorithmic_bytes": bpp * pixels_per_step,
             "peak_source": peak_src,
             "algorithmic_bytes_per_pixel": bpp,
             "kernel": "lk_march_kernel<true> (one launch per step)" if not wl["pyramidal"] else "whole pyramidal step (all launches)",

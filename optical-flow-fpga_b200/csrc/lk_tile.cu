@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
     float* fout_u = nullptr;
     float* fout_v = nullptr;
     if (SRC == SRC_WARP) {
-        const int cur = a.sel ? a.sel[pair] : 0;
+        const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
         fin_u = a.flow_u[cur] + pair * plane;
         fin_v = a.flow_v[cur] + pair * plane;
         fout_u = a.flow_u[cur ^ 1] + pair * plane;

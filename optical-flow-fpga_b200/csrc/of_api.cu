@@ -226,12 +226,18 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
     }
     auto flowA_u = [&](int k) { return k == 0 ? u : F(p.au_off[k]); };
     auto flowA_v = [&](int k) { return k == 0 ? v : F(p.av_off[k]); };
+    auto flow_u = [&](int k, int idx) { return idx ? F(p.bu_off[k]) : flowA_u(k); };
+    auto flow_v = [&](int k, int idx) { return idx ? F(p.bv_off[k]) : flowA_v(k); };
+    // Each iteration writes the other ping-pong buffer.  Starting every level in buffer
+    // (iterations & 1) makes a pair that runs all its iterations end in buffer 0, which at the
+    // finest level is the caller's (u, v): no final copy unless a pair stopped early.
+    const int start = iterations & 1;
 
     // zero flow at the coarsest level
     const int kc = levels - 1;
     const size_t coarse_bytes = (size_t)batch * p.h[kc] * p.w[kc] * sizeof(float);
-    OF_CUDA(cudaMemsetAsync(flowA_u(kc), 0, coarse_bytes, stream));
-    OF_CUDA(cudaMemsetAsync(flowA_v(kc), 0, coarse_bytes, stream));
+    OF_CUDA(cudaMemsetAsync(flow_u(kc, start), 0, coarse_bytes, stream));
+    OF_CUDA(cudaMemsetAsync(flow_v(kc, start), 0, coarse_bytes, stream));
 
     for (int k = kc; k >= 0; --k) {
         const int ref_level = kc - k;  // the reference counts levels from the coarsest
@@ -239,8 +245,8 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         int* done_k = done + (size_t)k * batch;
         if (k < kc) {
             OF_CUDA(launch_upsample_flow(flowA_u(k + 1), flowA_v(k + 1), F(p.bu_off[k + 1]), F(p.bv_off[k + 1]),
-                                         sel + (size_t)(k + 1) * batch, flowA_u(k), flowA_v(k), batch, p.h[k + 1],
-                                         p.w[k + 1], p.h[k], p.w[k], &cnt.n, stream));
+                                         sel + (size_t)(k + 1) * batch, start, flow_u(k, start), flow_v(k, start), batch,
+                                         p.h[k + 1], p.w[k + 1], p.h[k], p.w[k], &cnt.n, stream));
         }
         // fast mode: the register-marching kernel where the level allows TMA (width % 4 == 0,
         // window 5); otherwise, and always in exact mode, the reference-order tile kernel
@@ -253,6 +259,7 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         ra.flow_u[1] = F(p.bu_off[k]);
         ra.flow_v[1] = F(p.bv_off[k]);
         ra.sel = sel_k;
+        ra.sel_xor = start;
         ra.done = done_k;
         ra.partial = partial;
         ra.H = p.h[k];
@@ -271,6 +278,7 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                 a.flow_u[1] = F(p.bu_off[k]);
                 a.flow_v[1] = F(p.bv_off[k]);
                 a.sel = sel_k;
+                a.sel_xor = start;
                 a.done = done_k;
                 a.partial = partial;
                 a.H = p.h[k];
@@ -294,7 +302,8 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         }
     }
     // the finest level's current buffer -> caller's (u, v) (no-op for pairs already there)
-    OF_CUDA(launch_select_copy(u, v, F(p.bu_off[0]), F(p.bv_off[0]), sel, u, v, batch, (size_t)H * W, &cnt.n, stream));
+    OF_CUDA(launch_select_copy(u, v, F(p.bu_off[0]), F(p.bv_off[0]), sel, start, u, v, batch, (size_t)H * W, &cnt.n,
+                               stream));
     return OF_OK;
 }
 
@@ -504,7 +513,7 @@ int of_upsample_flow_f32(const float* coarse_u, const float* coarse_v, float* u,
     cudaStream_t st = g_streams[0];
     OF_CUDA(cudaMemcpyAsync(d[0], coarse_u, cb, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[1], coarse_v, cb, cudaMemcpyHostToDevice, st));
-    OF_CUDA(launch_upsample_flow(d[0], d[1], nullptr, nullptr, nullptr, d[2], d[3], 1, coarse_height, coarse_width,
+    OF_CUDA(launch_upsample_flow(d[0], d[1], nullptr, nullptr, nullptr, 0, d[2], d[3], 1, coarse_height, coarse_width,
                                  target_height, target_width, &cnt.n, st));
     OF_CUDA(cudaMemcpyAsync(u, d[2], tb, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaMemcpyAsync(v, d[3], tb, cudaMemcpyDeviceToHost, st));

@@ -28,6 +28,7 @@ struct RefineArgs {
     float* flow_u[2];   // ping-pong flow buffers, sel[pair] = index of the current one
     float* flow_v[2];
     const int* sel;
+    int sel_xor;        // current buffer = sel[pair] ^ sel_xor (lets a level start in buffer 1)
     const int* done;
     double* partial;    // [pair][units_per_pair][2]
     int H, W;
@@ -50,6 +51,7 @@ struct TileArgs {
     float* flow_u[2];
     float* flow_v[2];
     const int* sel;    // nullable: A is the input, B the output
+    int sel_xor;       // current buffer = sel[pair] ^ sel_xor
     const int* done;   // nullable: pairs whose level has converged are skipped
     double* partial;   // [pair][blocks_per_pair][2] sums of |du|, |dv| (SRC_WARP)
     // SRC_FRAMES / SRC_GRADS outputs
@@ -88,11 +90,12 @@ cudaError_t launch_warp(const float* img, const float* fu, const float* fv, floa
                         int* launches, cudaStream_t stream);
 // coarse flow (selected ping-pong buffer) -> fine grid, scaled (lucas_kanade_pyramidal.py:100-138)
 cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
-                                 const int* sel, float* fu, float* fv, int batch, int ch, int cw, int th, int tw,
-                                 int* launches, cudaStream_t stream);
+                                 const int* sel, int sel_xor, float* fu, float* fv, int batch, int ch, int cw, int th,
+                                 int tw, int* launches, cudaStream_t stream);
 // copy the selected ping-pong buffer of every pair to the caller's output
 cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1, const float* v1, const int* sel,
-                               float* out_u, float* out_v, int batch, size_t n, int* launches, cudaStream_t stream);
+                               int sel_xor, float* out_u, float* out_v, int batch, size_t n, int* launches,
+                               cudaStream_t stream);
 
 // ---- fixed-point mode (lk_fixed.cu) ----------------------------------------------------
 cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,

@@ -81,11 +81,27 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
     return m >= n ? period - 1 - m : m;
 }
 
+// One Gaussian output in SciPy's symmetric-kernel order: centre tap, then for k = R .. 1 the
+// pair (x[c-k] + x[c+k]) * w[R-k], everything float64, rounded to float32 by the caller.
+template <int R>
+__device__ __forceinline__ double gauss_tap_sum(const double* x, const double* w) {
+    double acc = dmul(x[R], w[R]);
+#pragma unroll
+    for (int ii = -R; ii < 0; ++ii) acc = dadd(acc, dmul(dadd(x[R + ii], x[R - ii]), w[ii + R]));
+    return acc;
+}
+
+// RADIUS > 0: sliding-window version (every input is read from shared memory and converted
+// to float64 once per run of SEG outputs).  RADIUS == 0: any radius <= PYR_MAX_RADIUS, one
+// output per thread and pass (only sigma != 2 gets here; the reference always uses sigma = 2).
+template <int RADIUS>
 __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
     extern __shared__ float smem[];
-    const int H = a.H, W = a.W, r = a.radius;
+    constexpr int SEG = 8;
+    const int H = a.H, W = a.W, r = RADIUS > 0 ? RADIUS : a.radius;
     const float* src = a.src + (size_t)blockIdx.z * H * W;
     float* dst = a.dst + (size_t)blockIdx.z * a.oh * a.ow;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     const int i0 = blockIdx.y * a.tile_h, j0 = blockIdx.x * a.tile_w;
     const int i1 = min(i0 + a.tile_h, a.oh) - 1, j1 = min(j0 + a.tile_w, a.ow) - 1;
@@ -96,37 +112,69 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
     const int fx_hi = min((int)floor(linspace_coord(j1, a.ow, W, a.step_x)) + 1, W - 1);
     const int R = fy_hi - fy_lo + 1, C = fx_hi - fx_lo + 1;
     const int IW = C + 2 * r, IH = R + 2 * r;
+    const int IWP = IW | 1;  // odd pitch: the axis-1 pass walks rows with lanes on different rows
 
-    float* img = smem;            // [IH][IW]   source with reflected halo
-    float* tmp = img + IH * IW;   // [R][IW]    after the axis-0 pass (float32)
-    float* smo = tmp + R * IW;    // [R][C]     after the axis-1 pass (float32)
+    float* img = smem;            // [IH][IW]    source with reflected halo
+    float* tmp = img + IH * IW;   // [R][IWP]    after the axis-0 pass (float32)
+    float* smo = tmp + R * IWP;   // [R][C]      after the axis-1 pass (float32)
 
-    for (int i = threadIdx.x; i < IH * IW; i += 256) {
-        const int y = reflect_index(fy_lo - r + i / IW, H);
-        const int x = reflect_index(fx_lo - r + i % IW, W);
-        img[i] = __ldg(src + (size_t)y * W + x);
+    for (int y = wid; y < IH; y += 8) {
+        const float* row = src + (size_t)reflect_index(fy_lo - r + y, H) * W;
+        for (int x = lane; x < IW; x += 32) img[y * IW + x] = __ldg(row + reflect_index(fx_lo - r + x, W));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < R * IW; i += 256) {
-        const int rr = i / IW, cc = i % IW;
-        const float* col = img + (rr + r) * IW + cc;
-        double acc = dmul((double)col[0], a.w[r]);
-        for (int ii = -r; ii < 0; ++ii)
-            acc = dadd(acc, dmul(dadd((double)col[ii * IW], (double)col[-ii * IW]), a.w[ii + r]));
-        tmp[i] = (float)acc;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < R * C; i += 256) {
-        const int rr = i / C, cc = i % C;
-        const float* row = tmp + rr * IW + cc + r;
-        double acc = dmul((double)row[0], a.w[r]);
-        for (int ii = -r; ii < 0; ++ii)
-            acc = dadd(acc, dmul(dadd((double)row[ii], (double)row[-ii]), a.w[ii + r]));
-        smo[i] = (float)acc;
+
+    if (RADIUS > 0) {
+        double w[2 * (RADIUS > 0 ? RADIUS : 1) + 1];
+#pragma unroll
+        for (int k = 0; k < 2 * RADIUS + 1; ++k) w[k] = a.w[k];
+        // axis 0: item = (row segment, column); consecutive lanes take consecutive columns
+        const int nseg_v = (R + SEG - 1) / SEG;
+        for (int item = tid; item < nseg_v * IW; item += 256) {
+            const int seg = item / IW, cc = item - seg * IW;
+            const int r0 = seg * SEG;
+            double x[SEG + 2 * (RADIUS > 0 ? RADIUS : 1)];
+#pragma unroll
+            for (int k = 0; k < SEG + 2 * RADIUS; ++k) x[k] = (double)img[min(r0 + k, IH - 1) * IW + cc];
+#pragma unroll
+            for (int k = 0; k < SEG; ++k)
+                if (r0 + k < R) tmp[(r0 + k) * IWP + cc] = (float)gauss_tap_sum<(RADIUS > 0 ? RADIUS : 1)>(x + k, w);
+        }
+        __syncthreads();
+        // axis 1: item = (column segment, row); consecutive lanes take consecutive rows
+        const int nseg_h = (C + SEG - 1) / SEG;
+        for (int item = tid; item < nseg_h * R; item += 256) {
+            const int seg = item / R, rr = item - seg * R;
+            const int c0 = seg * SEG;
+            double x[SEG + 2 * (RADIUS > 0 ? RADIUS : 1)];
+#pragma unroll
+            for (int k = 0; k < SEG + 2 * RADIUS; ++k) x[k] = (double)tmp[rr * IWP + min(c0 + k, IW - 1)];
+#pragma unroll
+            for (int k = 0; k < SEG; ++k)
+                if (c0 + k < C) smo[rr * C + c0 + k] = (float)gauss_tap_sum<(RADIUS > 0 ? RADIUS : 1)>(x + k, w);
+        }
+    } else {
+        for (int i = tid; i < R * IW; i += 256) {
+            const int rr = i / IW, cc = i % IW;
+            const float* col = img + (rr + r) * IW + cc;
+            double acc = dmul((double)col[0], a.w[r]);
+            for (int ii = -r; ii < 0; ++ii)
+                acc = dadd(acc, dmul(dadd((double)col[ii * IW], (double)col[-ii * IW]), a.w[ii + r]));
+            tmp[rr * IWP + cc] = (float)acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < R * C; i += 256) {
+            const int rr = i / C, cc = i % C;
+            const float* row = tmp + rr * IWP + cc + r;
+            double acc = dmul((double)row[0], a.w[r]);
+            for (int ii = -r; ii < 0; ++ii)
+                acc = dadd(acc, dmul(dadd((double)row[ii], (double)row[-ii]), a.w[ii + r]));
+            smo[i] = (float)acc;
+        }
     }
     __syncthreads();
     const int th = i1 - i0 + 1, tw = j1 - j0 + 1;
-    for (int o = threadIdx.x; o < th * tw; o += 256) {
+    for (int o = tid; o < th * tw; o += 256) {
         const int i = i0 + o / tw, j = j0 + o % tw;
         const double y = linspace_coord(i, a.oh, H, a.step_y);
         const double x = linspace_coord(j, a.ow, W, a.step_x);
@@ -173,17 +221,21 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
     if (a.tile_h > 16) a.tile_h = 16;
     if (a.tile_w > 32) a.tile_w = 32;
     const int IHmax = PYR_RMAX + 2 * radius, IWmax = PYR_CMAX + 2 * radius;
-    const size_t smem = (size_t)(IHmax * IWmax + PYR_RMAX * IWmax + PYR_RMAX * PYR_CMAX) * sizeof(float);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaError_t e =
-            cudaFuncSetAttribute(pyramid_down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)(IHmax * IWmax + PYR_RMAX * (IWmax + 1) + PYR_RMAX * PYR_CMAX) * sizeof(float);
+    static size_t attr_smem[2] = {0, 0};
+    const int which = radius == 8 ? 1 : 0;
+    if (smem > attr_smem[which]) {
+        cudaError_t e = which ? cudaFuncSetAttribute(pyramid_down_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(pyramid_down_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_smem = smem;
+        attr_smem[which] = smem;
     }
     if (launches) *launches += 1;
     dim3 grid((ow + a.tile_w - 1) / a.tile_w, (oh + a.tile_h - 1) / a.tile_h, batch);
-    pyramid_down_kernel<<<grid, 256, smem, stream>>>(a);
+    if (which)
+        pyramid_down_kernel<8><<<grid, 256, smem, stream>>>(a);  // sigma = 2, the reference's pyramid
+    else
+        pyramid_down_kernel<0><<<grid, 256, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -214,6 +266,7 @@ struct UpArgs {
     const float* cu[2];
     const float* cv[2];
     const int* sel;
+    int sel_xor;
     float* fu;
     float* fv;
     int ch, cw, th, tw;
@@ -221,31 +274,61 @@ struct UpArgs {
     float scale_y, scale_x;
 };
 
+// One thread = one target column and UP_ROWS target rows: the column's coordinate, taps and
+// weights are computed once, and u and v share every row's coordinate and weights.  The
+// linspace grid never leaves [0, n - 1], so every sample is inside the coarse field.
+constexpr int UP_ROWS = 8;
+
 __global__ void __launch_bounds__(256) upsample_flow_kernel(UpArgs a) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= a.tw || y >= a.th) return;
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= a.tw) return;
     const int pair = blockIdx.z;
-    const int cur = a.sel ? a.sel[pair] : 0;
+    const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
     const size_t cplane = (size_t)a.ch * a.cw;
-    const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
+    const float* __restrict__ cu = a.cu[cur] + pair * cplane;
+    const float* __restrict__ cv = a.cv[cur] + pair * cplane;
+    float* __restrict__ fu = a.fu + (size_t)pair * a.th * a.tw;
+    float* __restrict__ fv = a.fv + (size_t)pair * a.th * a.tw;
+
     const double xc = linspace_coord(x, a.tw, a.cw, a.step_x);
-    const float u = bilinear_f64(a.cu[cur] + pair * cplane, a.ch, a.cw, yc, xc);
-    const float v = bilinear_f64(a.cv[cur] + pair * cplane, a.ch, a.cw, yc, xc);
-    const size_t o = (size_t)pair * a.th * a.tw + (size_t)y * a.tw + x;
-    a.fu[o] = fmul(u, a.scale_x);  // flow scales with the resolution, float32 multiply
-    a.fv[o] = fmul(v, a.scale_y);
+    const double fx0 = floor(xc);
+    const double fx = dsub(xc, fx0), wx0 = dsub(1.0, fx);
+    const int x0 = (int)fx0;
+    const int x1 = min(x0 + 1, a.cw - 1);  // weight 0 when it would leave the field
+    const int y_begin = blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.th);
+    for (int y = y_begin; y < y_end; ++y) {
+        const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
+        const double fy0 = floor(yc);
+        const double fy = dsub(yc, fy0), wy0 = dsub(1.0, fy);
+        const int y0 = (int)fy0;
+        const int y1 = min(y0 + 1, a.ch - 1);
+        const size_t r0 = (size_t)y0 * a.cw, r1 = (size_t)y1 * a.cw;
+        // map_coordinates order: taps row-major, each (value * wy) * wx, summed from 0.0
+        double tu = 0.0, tv = 0.0;
+        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r0 + x0), wy0), wx0));
+        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r0 + x1), wy0), fx));
+        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r1 + x0), fy), wx0));
+        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r1 + x1), fy), fx));
+        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r0 + x0), wy0), wx0));
+        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r0 + x1), wy0), fx));
+        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r1 + x0), fy), wx0));
+        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r1 + x1), fy), fx));
+        const size_t o = (size_t)y * a.tw + x;
+        fu[o] = fmul((float)tu, a.scale_x);  // flow scales with the resolution, float32 multiply
+        fv[o] = fmul((float)tv, a.scale_y);
+    }
 }
 
 cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
-                                 const int* sel, float* fu, float* fv, int batch, int ch, int cw, int th, int tw,
-                                 int* launches, cudaStream_t stream) {
+                                 const int* sel, int sel_xor, float* fu, float* fv, int batch, int ch, int cw, int th,
+                                 int tw, int* launches, cudaStream_t stream) {
     UpArgs a;
     a.cu[0] = cu0;
     a.cv[0] = cv0;
     a.cu[1] = cu1 ? cu1 : cu0;
     a.cv[1] = cv1 ? cv1 : cv0;
     a.sel = sel;
+    a.sel_xor = sel_xor;
     a.fu = fu;
     a.fv = fv;
     a.ch = ch;
@@ -257,17 +340,18 @@ cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float
     a.scale_y = (float)((double)th / (double)ch);
     a.scale_x = (float)((double)tw / (double)cw);
     if (launches) *launches += 1;
-    dim3 grid((tw + 63) / 64, (th + 3) / 4, batch);
+    dim3 grid((tw + 255) / 256, (th + UP_ROWS - 1) / UP_ROWS, batch);
     upsample_flow_kernel<<<grid, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) select_copy_kernel(const float* __restrict__ u0, const float* __restrict__ v0,
                                                            const float* __restrict__ u1, const float* __restrict__ v1,
-                                                           const int* __restrict__ sel, float* __restrict__ out_u,
-                                                           float* __restrict__ out_v, size_t n) {
+                                                           const int* __restrict__ sel, int sel_xor,
+                                                           float* __restrict__ out_u, float* __restrict__ out_v,
+                                                           size_t n) {
     const int pair = blockIdx.y;
-    const int cur = sel ? sel[pair] : 0;
+    const int cur = (sel ? sel[pair] : 0) ^ sel_xor;
     const float* su = (cur ? u1 : u0) + pair * n;
     const float* sv = (cur ? v1 : v0) + pair * n;
     if (su == out_u + pair * n) return;  // already in place
@@ -278,13 +362,14 @@ __global__ void __launch_bounds__(256) select_copy_kernel(const float* __restric
 }
 
 cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1, const float* v1, const int* sel,
-                               float* out_u, float* out_v, int batch, size_t n, int* launches, cudaStream_t stream) {
+                               int sel_xor, float* out_u, float* out_v, int batch, size_t n, int* launches,
+                               cudaStream_t stream) {
     if (launches) *launches += 1;
     unsigned bx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 4096) bx = 4096;
     dim3 grid(bx, batch);
-    select_copy_kernel<<<grid, 256, 0, stream>>>(u0, v0, u1, v1, sel, out_u, out_v, n);
+    select_copy_kernel<<<grid, 256, 0, stream>>>(u0, v0, u1, v1, sel, sel_xor, out_u, out_v, n);
     return cudaGetLastError();
 }
 
