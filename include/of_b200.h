@@ -122,6 +122,34 @@ int of_lk_pyramidal_f32_dev(const float* prev, const float* curr, float* u, floa
                             size_t workspace_bytes, int* iters_executed_dev, float* residuals_dev,
                             void* stream);
 
+/* ---- building blocks of the pyramidal path on device buffers (row-band multi-GPU mode) ---
+ * A rank of a row-band job holds full-size frames / flow planes but computes only its rows.
+ * All four calls only enqueue work on `stream`. */
+
+/* one coarser pyramid level for a batch (device version of of_pyramid_down_f32) */
+int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height, int width,
+                            int out_height, int out_width, const double* weights, int radius,
+                            void* stream);
+
+/* upsample_flow for target rows [row_lo, row_hi) only */
+int of_upsample_flow_f32_dev(const float* coarse_u, const float* coarse_v, float* u, float* v,
+                             int batch, int coarse_height, int coarse_width, int target_height,
+                             int target_width, int row_lo, int row_hi, void* stream);
+
+size_t of_lk_refine_workspace_bytes(int batch, int height, int width);
+
+/* One refinement iteration of lucas_kanade_pyramidal (lucas_kanade_pyramidal.py:203-214) on rows
+ * [row_lo, row_hi) of a level:  flow_out = flow_in + LK(prev, warp(curr, flow_in)).
+ * flow_in must be valid on rows [row_lo - 3, row_hi + 3) (clipped to the frame); rows outside
+ * [row_lo, row_hi) of flow_out are left untouched.  sums[pair][2] receives sum|du|, sum|dv|
+ * over rows [own_lo, own_hi) (float64) -- the caller reduces them over ranks and applies the
+ * reference's convergence test.  row_lo must be even. */
+int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow_in_u,
+                         const float* flow_in_v, float* flow_out_u, float* flow_out_v, int batch,
+                         int height, int width, int window, int mode, int row_lo, int row_hi,
+                         int own_lo, int own_hi, double* sums, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
                               int batch, int height, int width, int flags, void* stream);
 

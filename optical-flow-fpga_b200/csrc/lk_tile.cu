@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
 
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
-    const int ox = blockIdx.x * TX, oy = blockIdx.y * TY;
+    const int ox = blockIdx.x * TX, oy = (SRC == SRC_WARP ? a.row_lo : 0) + blockIdx.y * TY;
+    const int y_end = (SRC == SRC_WARP) ? a.row_hi : H;
     const int tid = threadIdx.x;
 
     const float* fin_u = nullptr;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
     for (int o = tid; o < TY * TX; o += TILE_THREADS) {
         const int r = o / TX, c = o % TX;
         const int y = oy + r, x = ox + c;
-        if (y >= H || x >= W) continue;
+        if (y >= y_end || x >= W) continue;
         float u = 0.0f, v = 0.0f;
         if (y >= HW && y < H - HW && x >= HW && x < W - HW) {
             const float* wx = gx + r * GW + c;
@@ -175,8 +176,10 @@ __global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
         if (SRC == SRC_WARP) {
             fout_u[go] = fadd(__ldg(fin_u + go), u);  // flow += d
             fout_v[go] = fadd(__ldg(fin_v + go), v);
-            acc_u += (double)fabsf(u);
-            acc_v += (double)fabsf(v);
+            if (y >= a.own_lo && y < a.own_hi) {
+                acc_u += (double)fabsf(u);
+                acc_v += (double)fabsf(v);
+            }
         } else {
             a.out_u[pair * plane + go] = u;
             a.out_v[pair * plane + go] = v;
@@ -253,7 +256,47 @@ __global__ void __launch_bounds__(256) iter_finalize_kernel(IterFinalizeArgs a) 
 
 bool lk_tile_window_supported(int window) { return window >= 1 && window <= 11 && (window & 1); }
 
-int lk_tile_blocks_per_pair(int H, int W) { return ((W + TX - 1) / TX) * ((H + TY - 1) / TY); }
+int lk_tile_blocks_per_pair(int rows, int W) { return ((W + TX - 1) / TX) * ((rows + TY - 1) / TY); }
+
+// per pair: fixed-order float64 sum of the per-block partials -> sums[pair][2]
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partial, int blocks_per_pair,
+                                                            double* __restrict__ sums) {
+    const int pair = blockIdx.x;
+    __shared__ double red[2][8];
+    const double* part = partial + (size_t)pair * blocks_per_pair * 2;
+    double su = 0.0, sv = 0.0;
+    for (int i = threadIdx.x; i < blocks_per_pair; i += 256) {
+        su += part[2 * i];
+        sv += part[2 * i + 1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        su += __shfl_down_sync(0xffffffffu, su, off);
+        sv += __shfl_down_sync(0xffffffffu, sv, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = su;
+        red[1][threadIdx.x >> 5] = sv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        su = 0.0;
+        sv = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            su += red[0][w];
+            sv += red[1][w];
+        }
+        sums[2 * pair] = su;
+        sums[2 * pair + 1] = sv;
+    }
+}
+
+cudaError_t launch_sum_partials(const double* partial, int blocks_per_pair, double* sums, int batch, int* launches,
+                                cudaStream_t stream) {
+    if (launches) *launches += 1;
+    sum_partials_kernel<<<batch, 256, 0, stream>>>(partial, blocks_per_pair, sums);
+    return cudaGetLastError();
+}
 
 template <int SRC, int WIN>
 static cudaError_t launch_one(const TileArgs& a, int batch, cudaStream_t stream) {
@@ -261,7 +304,9 @@ static cudaError_t launch_one(const TileArgs& a, int batch, cudaStream_t stream)
     constexpr int GW = TX + 2 * HW, GH = TY + 2 * HW;
     constexpr int FW = GW + 2, FH = GH + 2;
     const size_t smem = (size_t)(3 * GH * GW + 2 * FH * FW) * sizeof(float);
-    dim3 grid((a.W + TX - 1) / TX, (a.H + TY - 1) / TY, batch);
+    const int rows = (SRC == SRC_WARP) ? a.row_hi - a.row_lo : a.H;
+    if (rows <= 0) return cudaErrorInvalidValue;
+    dim3 grid((a.W + TX - 1) / TX, (rows + TY - 1) / TY, batch);
     lk_tile_kernel<SRC, WIN><<<grid, TILE_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }

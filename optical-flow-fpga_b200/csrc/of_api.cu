@@ -246,7 +246,7 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         if (k < kc) {
             OF_CUDA(launch_upsample_flow(flowA_u(k + 1), flowA_v(k + 1), F(p.bu_off[k + 1]), F(p.bv_off[k + 1]),
                                          sel + (size_t)(k + 1) * batch, start, flow_u(k, start), flow_v(k, start), batch,
-                                         p.h[k + 1], p.w[k + 1], p.h[k], p.w[k], &cnt.n, stream));
+                                         p.h[k + 1], p.w[k + 1], p.h[k], p.w[k], 0, p.h[k], &cnt.n, stream));
         }
         // fast mode: the register-marching kernel where the level allows TMA (width % 4 == 0,
         // window 5); otherwise, and always in exact mode, the reference-order tile kernel
@@ -264,6 +264,10 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         ra.partial = partial;
         ra.H = p.h[k];
         ra.W = p.w[k];
+        ra.row_lo = 0;
+        ra.row_hi = p.h[k];
+        ra.own_lo = 0;
+        ra.own_hi = p.h[k];
         const bool fast_level = (mode == OF_MODE_FAST) && lk_refine_supported(ra, window);
         for (int it = 0; it < iterations; ++it) {
             if (fast_level) {
@@ -283,6 +287,10 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                 a.partial = partial;
                 a.H = p.h[k];
                 a.W = p.w[k];
+                a.row_lo = 0;
+                a.row_hi = p.h[k];
+                a.own_lo = 0;
+                a.own_hi = p.h[k];
                 OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
             }
             IterFinalizeArgs f;
@@ -514,7 +522,7 @@ int of_upsample_flow_f32(const float* coarse_u, const float* coarse_v, float* u,
     OF_CUDA(cudaMemcpyAsync(d[0], coarse_u, cb, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[1], coarse_v, cb, cudaMemcpyHostToDevice, st));
     OF_CUDA(launch_upsample_flow(d[0], d[1], nullptr, nullptr, nullptr, 0, d[2], d[3], 1, coarse_height, coarse_width,
-                                 target_height, target_width, &cnt.n, st));
+                                 target_height, target_width, 0, target_height, &cnt.n, st));
     OF_CUDA(cudaMemcpyAsync(u, d[2], tb, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaMemcpyAsync(v, d[3], tb, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaStreamSynchronize(st));
@@ -596,6 +604,103 @@ int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v
                                     (size_t)nb * levels * iterations * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
         OF_CUDA(cudaStreamSynchronize(st));
     }
+    return OF_OK;
+}
+
+int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height, int width, int out_height,
+                            int out_width, const double* weights, int radius, void* stream) {
+    OF_TRY(check_frame(src, dst, height, width));
+    if (out_height < 1 || out_width < 1) return fail(OF_ERR_INVALID_ARGUMENT, "output size must be >= 1");
+    if (!weights || radius < 0 || radius > OF_MAX_GAUSS_RADIUS)
+        return fail(OF_ERR_INVALID_ARGUMENT, "gaussian weights missing or radius out of range");
+    if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
+    OF_TRY(need_device());
+    Counter cnt;
+    OF_CUDA(launch_pyramid_down(src, dst, batch, height, width, out_height, out_width, weights, radius, &cnt.n,
+                                static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+int of_upsample_flow_f32_dev(const float* coarse_u, const float* coarse_v, float* u, float* v, int batch,
+                             int coarse_height, int coarse_width, int target_height, int target_width, int row_lo,
+                             int row_hi, void* stream) {
+    OF_TRY(check_frame(coarse_u, coarse_v, coarse_height, coarse_width));
+    OF_TRY(check_frame(u, v, target_height, target_width));
+    if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
+    if (row_lo < 0 || row_hi > target_height || row_lo >= row_hi)
+        return fail(OF_ERR_INVALID_ARGUMENT, "bad target row range");
+    OF_TRY(need_device());
+    Counter cnt;
+    OF_CUDA(launch_upsample_flow(coarse_u, coarse_v, nullptr, nullptr, nullptr, 0, u, v, batch, coarse_height,
+                                 coarse_width, target_height, target_width, row_lo, row_hi, &cnt.n,
+                                 static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+size_t of_lk_refine_workspace_bytes(int batch, int height, int width) {
+    if (batch < 1 || height < 1 || width < 1) return 0;
+    return align_up((size_t)batch * lk_tile_blocks_per_pair(height, width) * 2 * sizeof(double));
+}
+
+int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow_in_u, const float* flow_in_v,
+                         float* flow_out_u, float* flow_out_v, int batch, int height, int width, int window, int mode,
+                         int row_lo, int row_hi, int own_lo, int own_hi, double* sums, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(flow_in_u, flow_in_v, height, width));
+    OF_TRY(check_frame(flow_out_u, flow_out_v, height, width));
+    OF_TRY(check_window(window));
+    if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
+    if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
+    if (row_lo < 0 || row_hi > height || row_lo >= row_hi || (row_lo & 1))
+        return fail(OF_ERR_INVALID_ARGUMENT, "bad row range (row_lo must be even)");
+    if (flow_in_u == flow_out_u || flow_in_v == flow_out_v)
+        return fail(OF_ERR_INVALID_ARGUMENT, "flow_in and flow_out must be different buffers");
+    if (!sums || !workspace || workspace_bytes < of_lk_refine_workspace_bytes(batch, height, width))
+        return fail(OF_ERR_INVALID_ARGUMENT, "sums / workspace missing or too small");
+    OF_TRY(need_device());
+    Counter cnt;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* partial = static_cast<double*>(workspace);
+    RefineArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.prev = prev;
+    ra.curr = curr;
+    ra.flow_u[0] = const_cast<float*>(flow_in_u);
+    ra.flow_v[0] = const_cast<float*>(flow_in_v);
+    ra.flow_u[1] = flow_out_u;
+    ra.flow_v[1] = flow_out_v;
+    ra.partial = partial;
+    ra.H = height;
+    ra.W = width;
+    ra.row_lo = row_lo;
+    ra.row_hi = row_hi;
+    ra.own_lo = own_lo;
+    ra.own_hi = own_hi;
+    int blocks;
+    if (mode == OF_MODE_FAST && lk_refine_supported(ra, window)) {
+        OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, st));
+        blocks = lk_refine_units_per_pair(batch, row_hi - row_lo, width);
+    } else {
+        TileArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in0 = prev;
+        a.in1 = curr;
+        a.flow_u[0] = ra.flow_u[0];
+        a.flow_v[0] = ra.flow_v[0];
+        a.flow_u[1] = flow_out_u;
+        a.flow_v[1] = flow_out_v;
+        a.partial = partial;
+        a.H = height;
+        a.W = width;
+        a.row_lo = row_lo;
+        a.row_hi = row_hi;
+        a.own_lo = own_lo;
+        a.own_hi = own_hi;
+        OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, st));
+        blocks = lk_tile_blocks_per_pair(row_hi - row_lo, width);
+    }
+    OF_CUDA(launch_sum_partials(partial, blocks, sums, batch, &cnt.n, st));
     return OF_OK;
 }
 

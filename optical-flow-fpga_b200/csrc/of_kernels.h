@@ -32,11 +32,15 @@ struct RefineArgs {
     const int* done;
     double* partial;    // [pair][units_per_pair][2]
     int H, W;
+    // Row-band mode: only rows [row_lo, row_hi) are computed (the frame and the flow buffers are
+    // still full-size), and only rows [own_lo, own_hi) enter the |du|, |dv| sums.  Whole frame:
+    // 0, H, 0, H.  row_lo must be even so that rows pair up the same way on every rank.
+    int row_lo, row_hi, own_lo, own_hi;
     int n_strips, n_bands, band_rows;  // filled by the launcher
     long long n_units;
 };
 bool lk_refine_supported(const RefineArgs& a, int window);
-int lk_refine_units_per_pair(int batch, int H, int W);
+int lk_refine_units_per_pair(int batch, int rows, int W);
 cudaError_t launch_lk_refine(const RefineArgs& a, int batch, int* launches, cudaStream_t stream);
 
 // ---- K1/K3 exact: tile kernel in the reference's operation order (lk_tile.cu) ----------
@@ -58,9 +62,10 @@ struct TileArgs {
     float* out_u;
     float* out_v;
     int H, W;
+    int row_lo, row_hi, own_lo, own_hi;  // SRC_WARP row-band mode (see RefineArgs); else 0, H, 0, H
 };
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream);
-int lk_tile_blocks_per_pair(int H, int W);
+int lk_tile_blocks_per_pair(int rows, int W);
 bool lk_tile_window_supported(int window);
 
 // after one refinement iteration: reduce the per-block partial sums, decide convergence,
@@ -78,6 +83,10 @@ struct IterFinalizeArgs {
     int iteration;
 };
 cudaError_t launch_iter_finalize(const IterFinalizeArgs& a, int batch, int* launches, cudaStream_t stream);
+// row-band mode: just the per-pair sums (sum|du|, sum|dv| over this rank's rows) -> sums[pair][2];
+// the ranks all-reduce them and take the decision on the host side of the C ABI
+cudaError_t launch_sum_partials(const double* partial, int blocks_per_pair, double* sums, int batch, int* launches,
+                                cudaStream_t stream);
 
 // ---- helper kernels (pyramid.cu) -------------------------------------------------------
 cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, float* iy, float* it, int batch, int H,
@@ -91,7 +100,7 @@ cudaError_t launch_warp(const float* img, const float* fu, const float* fv, floa
 // coarse flow (selected ping-pong buffer) -> fine grid, scaled (lucas_kanade_pyramidal.py:100-138)
 cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
                                  const int* sel, int sel_xor, float* fu, float* fv, int batch, int ch, int cw, int th,
-                                 int tw, int* launches, cudaStream_t stream);
+                                 int tw, int row_lo, int row_hi, int* launches, cudaStream_t stream);
 // copy the selected ping-pong buffer of every pair to the caller's output
 cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1, const float* v1, const int* sel,
                                int sel_xor, float* out_u, float* out_v, int batch, size_t n, int* launches,

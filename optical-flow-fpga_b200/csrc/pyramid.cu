@@ -270,6 +270,7 @@ struct UpArgs {
     float* fu;
     float* fv;
     int ch, cw, th, tw;
+    int row_lo, row_hi;  // target rows to produce
     double step_y, step_x;
     float scale_y, scale_x;
 };
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(256) upsample_flow_kernel(UpArgs a) {
     const double fx = dsub(xc, fx0), wx0 = dsub(1.0, fx);
     const int x0 = (int)fx0;
     const int x1 = min(x0 + 1, a.cw - 1);  // weight 0 when it would leave the field
-    const int y_begin = blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.th);
+    const int y_begin = a.row_lo + blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.row_hi);
     for (int y = y_begin; y < y_end; ++y) {
         const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
         const double fy0 = floor(yc);
@@ -321,7 +322,8 @@ __global__ void __launch_bounds__(256) upsample_flow_kernel(UpArgs a) {
 
 cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
                                  const int* sel, int sel_xor, float* fu, float* fv, int batch, int ch, int cw, int th,
-                                 int tw, int* launches, cudaStream_t stream) {
+                                 int tw, int row_lo, int row_hi, int* launches, cudaStream_t stream) {
+    if (row_lo < 0 || row_hi > th || row_lo >= row_hi) return cudaErrorInvalidValue;
     UpArgs a;
     a.cu[0] = cu0;
     a.cv[0] = cv0;
@@ -335,12 +337,14 @@ cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float
     a.cw = cw;
     a.th = th;
     a.tw = tw;
+    a.row_lo = row_lo;
+    a.row_hi = row_hi;
     a.step_y = th > 1 ? (double)(ch - 1) / (double)(th - 1) : 0.0;
     a.step_x = tw > 1 ? (double)(cw - 1) / (double)(tw - 1) : 0.0;
     a.scale_y = (float)((double)th / (double)ch);
     a.scale_x = (float)((double)tw / (double)cw);
     if (launches) *launches += 1;
-    dim3 grid((tw + 255) / 256, (th + UP_ROWS - 1) / UP_ROWS, batch);
+    dim3 grid((tw + 255) / 256, (row_hi - row_lo + UP_ROWS - 1) / UP_ROWS, batch);
     upsample_flow_kernel<<<grid, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }

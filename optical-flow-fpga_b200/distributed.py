@@ -124,3 +124,229 @@ def lk_single_scale_rowbands(
         return u, v
     counts = [p[1] - p[0] for p in plan]
     return _all_gather_rows(np.ascontiguousarray(u), counts), _all_gather_rows(np.ascontiguousarray(v), counts)
+
+
+# ======================================================================================
+# Row-band mode for the PYRAMIDAL path (BASELINE config 5: one very large frame pair)
+# ======================================================================================
+#
+# Every rank keeps full-size level images and flow planes but computes only its band of rows.
+# Inside a level there is NO halo exchange: iteration i of I is computed on the band extended
+# by GROW * (I - 1 - i) rows on both sides (a refinement iteration reads flow_in 3 rows beyond
+# the rows it writes; GROW = 4 leaves one row for the even alignment of the band start), so
+# after the last iteration exactly the owned rows are still valid.  Communication happens
+#   * once per iteration: all-reduce of (sum|du|, sum|dv|) over the owned rows -- 16 bytes,
+#     needed for the reference's global early exit (lucas_kanade_pyramidal.py:213-223);
+#   * once per level: all-gather of the owned flow rows, which feeds the next level's
+#     upsampling (its taps and the next level's extended band reach into neighbour bands)
+#     and, at the finest level, is the final gather.
+# The warp gather has unbounded reach, so the current frame's pyramid is replicated (every
+# rank builds both pyramids itself; they cost far less than the iterations).
+#
+# Backends: `CudaBackend` (torch CUDA tensors + the `_dev` C-ABI calls) is the product path;
+# the split / collective logic is backend-agnostic so that tests can drive it on CPU tensors.
+
+GROW = 4
+
+
+class SingleProcessComm:
+    rank, world = 0, 1
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_gather_rows(self, local_rows, counts):
+        return local_rows
+
+
+class TorchDistComm:
+    """torch.distributed default group: NCCL for CUDA tensors, gloo for CPU tensors."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t)
+        return t
+
+    def all_gather_rows(self, local_rows, counts):
+        import torch
+
+        mx = max(counts)
+        pad = torch.zeros((mx,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+        pad[: local_rows.shape[0]] = local_rows
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad)
+        return torch.cat([o[:n] for o, n in zip(out, counts)], dim=0)
+
+
+class ThreadComm:
+    """R ranks as threads of one process (tests: emulate a multi-rank job on one device)."""
+
+    def __init__(self, world: int):
+        import threading
+
+        self.world = world
+        self._barrier = threading.Barrier(world)
+        self._slots = [None] * world
+
+    def view(self, rank: int):
+        parent = self
+
+        class _View:
+            world = parent.world
+
+            def __init__(self, r):
+                self.rank = r
+
+            def _exchange(self, item):
+                parent._slots[self.rank] = item
+                parent._barrier.wait()
+                items = list(parent._slots)
+                parent._barrier.wait()
+                return items
+
+            def all_reduce_sum(self, t):
+                items = self._exchange(t.clone())
+                total = items[0].clone()
+                for it in items[1:]:
+                    total += it.to(total.device)
+                return total
+
+            def all_gather_rows(self, local_rows, counts):
+                import torch
+
+                items = self._exchange(local_rows.clone())
+                return torch.cat([it.to(local_rows.device) for it in items], dim=0)
+
+        return _View(rank)
+
+
+class CudaBackend:
+    """Device arrays are torch CUDA tensors; arithmetic is the C-ABI `_dev` entry points."""
+
+    def __init__(self, device=None):
+        import torch
+
+        import of_b200
+
+        self.torch, self.ofb = torch, of_b200
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self._ws = None
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def from_host(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+
+    def to_host(self, t):
+        return t.cpu().numpy()
+
+    def empty(self, h, w):
+        return self.torch.empty((h, w), dtype=self.torch.float32, device=self.device)
+
+    def zeros(self, h, w):
+        return self.torch.zeros((h, w), dtype=self.torch.float32, device=self.device)
+
+    def pyramid_down(self, img):
+        h, w = img.shape
+        out = self.empty(int(h * 0.5), int(w * 0.5))
+        self.ofb.pyramid_down_dev(img.data_ptr(), out.data_ptr(), 1, h, w, out.shape[0], out.shape[1], self._stream())
+        return out
+
+    def upsample(self, cu, cv, th, tw, lo, hi):
+        u, v = self.empty(th, tw), self.empty(th, tw)
+        self.ofb.upsample_flow_dev(cu.data_ptr(), cv.data_ptr(), u.data_ptr(), v.data_ptr(), 1, cu.shape[0], cu.shape[1],
+                                   th, tw, lo, hi, self._stream())
+        return u, v
+
+    def refine(self, prev, curr, fin_u, fin_v, fout_u, fout_v, window, mode, lo, hi, own_lo, own_hi):
+        h, w = prev.shape
+        need = self.ofb.lk_refine_workspace_bytes(1, h, w)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        sums = self.torch.zeros(2, dtype=self.torch.float64, device=self.device)
+        self.ofb.lk_refine_dev(prev.data_ptr(), curr.data_ptr(), fin_u.data_ptr(), fin_v.data_ptr(), fout_u.data_ptr(),
+                               fout_v.data_ptr(), 1, h, w, window, mode, lo, hi, own_lo, own_hi, sums.data_ptr(),
+                               self._ws.data_ptr(), self._ws.numel(), self._stream())
+        return sums
+
+    def zero_sums(self):
+        return self.torch.zeros(2, dtype=self.torch.float64, device=self.device)
+
+
+def lk_pyramidal_rowbands(
+    frame_prev: np.ndarray,
+    frame_curr: np.ndarray,
+    num_levels: int = 3,
+    window_size: int = 5,
+    num_iterations: int = 3,
+    mode: Optional[int] = None,
+    comm=None,
+    backend=None,
+    trace: Optional[list] = None,
+):
+    """Pyramidal LK of ONE [H, W] frame pair with the rows of every level split over the ranks.
+    Every rank returns the full (u, v).  Results equal the single-GPU path bit for bit (same
+    kernels, same row pairing); the early-exit decision uses the all-reduced residual sums."""
+    if comm is None:
+        comm = TorchDistComm() if _dist() is not None else SingleProcessComm()
+    if backend is None:
+        backend = CudaBackend()
+    if mode is None:
+        import of_b200
+
+        mode = of_b200.default_mode()
+    rank, world = comm.rank, comm.world
+    halo = window_size // 2 + 1
+    if halo > GROW - 1:
+        raise ValueError("row-band mode supports window_size <= 5")
+    iters = int(num_iterations)
+
+    lv_prev = [backend.from_host(frame_prev)]
+    lv_curr = [backend.from_host(frame_curr)]
+    for _ in range(1, int(num_levels)):
+        lv_prev.insert(0, backend.pyramid_down(lv_prev[0]))
+        lv_curr.insert(0, backend.pyramid_down(lv_curr[0]))
+
+    h, w = lv_prev[0].shape
+    flow_u, flow_v = backend.zeros(h, w), backend.zeros(h, w)
+    for level, (img_prev, img_curr) in enumerate(zip(lv_prev, lv_curr)):
+        h, w = img_prev.shape
+        a, b = shard_range(h, rank, world)
+        reach = GROW * max(iters, 1) + GROW
+        if level > 0:
+            lo, hi = max(0, a - reach), min(h, b + reach)
+            if b > a:
+                flow_u, flow_v = backend.upsample(flow_u, flow_v, h, w, lo, hi)
+            else:
+                flow_u, flow_v = backend.empty(h, w), backend.empty(h, w)
+        out_u, out_v = backend.empty(h, w), backend.empty(h, w)
+        for it in range(iters):
+            ext = GROW * (iters - 1 - it)
+            lo = max(0, a - ext)
+            lo -= lo & 1  # even: rows pair up identically on every rank
+            hi = min(h, b + ext)
+            if b > a:
+                sums = backend.refine(img_prev, img_curr, flow_u, flow_v, out_u, out_v, window_size, mode, lo, hi, a, b)
+            else:
+                sums = backend.zero_sums()
+            sums = comm.all_reduce_sum(sums)
+            s = sums.detach().cpu().numpy() if hasattr(sums, "detach") else np.asarray(sums)
+            n = float(h) * float(w)
+            mean_du, mean_dv = np.float32(s[0] / n), np.float32(s[1] / n)
+            if trace is not None:
+                trace.append((level, it, float(mean_du), float(mean_dv)))
+            flow_u, out_u = out_u, flow_u
+            flow_v, out_v = out_v, flow_v
+            if mean_du < np.float32(0.01) and mean_dv < np.float32(0.01):
+                break
+        if world > 1:
+            counts = [shard_range(h, r, world)[1] - shard_range(h, r, world)[0] for r in range(world)]
+            flow_u = comm.all_gather_rows(flow_u[a:b].contiguous(), counts)
+            flow_v = comm.all_gather_rows(flow_v[a:b].contiguous(), counts)
+    return backend.to_host(flow_u), backend.to_host(flow_v)

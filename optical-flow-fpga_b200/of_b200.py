@@ -71,6 +71,13 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, C.c_size_t, _vp, _vp, _vp],
     ),
     "of_lk_single_scale_fx_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "of_pyramid_down_f32_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "of_upsample_flow_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "of_lk_refine_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "of_lk_refine_f32_dev": (
+        _i,
+        [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp],
+    ),
 }
 
 
@@ -339,6 +346,39 @@ def lk_pyramidal_dev(
         lib().of_lk_pyramidal_f32_dev(
             prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, levels, _window(window_size), iterations, mode,
             _ptr(wts), (len(wts) - 1) // 2, workspace_ptr, workspace_bytes, iters_ptr, resid_ptr, stream,
+        )
+    )
+
+
+def pyramid_down_dev(src_ptr, dst_ptr, batch, height, width, out_height, out_width, stream=0, sigma: float = 2.0):
+    wts = gaussian_weights(sigma)
+    _check(
+        lib().of_pyramid_down_f32_dev(
+            src_ptr, dst_ptr, batch, height, width, out_height, out_width, _ptr(wts), (len(wts) - 1) // 2, stream
+        )
+    )
+
+
+def upsample_flow_dev(cu_ptr, cv_ptr, u_ptr, v_ptr, batch, ch, cw, th, tw, row_lo=0, row_hi=None, stream=0):
+    _check(
+        lib().of_upsample_flow_f32_dev(
+            cu_ptr, cv_ptr, u_ptr, v_ptr, batch, ch, cw, th, tw, row_lo, th if row_hi is None else row_hi, stream
+        )
+    )
+
+
+def lk_refine_workspace_bytes(batch, height, width) -> int:
+    return int(lib().of_lk_refine_workspace_bytes(batch, height, width))
+
+
+def lk_refine_dev(
+    prev_ptr, curr_ptr, fin_u_ptr, fin_v_ptr, fout_u_ptr, fout_v_ptr, batch, height, width, window_size, mode,
+    row_lo, row_hi, own_lo, own_hi, sums_ptr, workspace_ptr, workspace_bytes, stream=0,
+):
+    _check(
+        lib().of_lk_refine_f32_dev(
+            prev_ptr, curr_ptr, fin_u_ptr, fin_v_ptr, fout_u_ptr, fout_v_ptr, batch, height, width,
+            _window(window_size), mode, row_lo, row_hi, own_lo, own_hi, sums_ptr, workspace_ptr, workspace_bytes, stream,
         )
     )
 

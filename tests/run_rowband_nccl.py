@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Real multi-GPU check of the row-band pyramidal mode (NCCL), run under torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/run_rowband_nccl.py [--height 4320 --width 7680 --levels 5 --iters 10]
+
+Every rank computes its row bands; rank 0 compares the gathered flow with the single-GPU
+result of the same frames (bit for bit) and prints timings."""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "optical-flow-fpga_b200")):
+    sys.path.insert(0, p)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import distributed as ofd
+    import of_b200
+    import synthetic
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--mode", choices=["exact", "fast"], default="fast")
+    ap.add_argument("--repeat", type=int, default=3)
+    args = ap.parse_args()
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    of_b200.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = of_b200.MODE_FAST if args.mode == "fast" else of_b200.MODE_EXACT
+    prev, curr, _ = synthetic.make_pairs_numpy(1, args.height, args.width, seed=77)
+    p, c = prev[0], np.roll(curr[0], 2, axis=0)
+    times = []
+    for _ in range(args.repeat):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        u, v = ofd.lk_pyramidal_rowbands(p, c, args.levels, 5, args.iters, mode=mode)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    ok = None
+    t_single = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        u1, v1 = of_b200.lk_pyramidal(p, c, args.levels, 5, args.iters, mode=mode)
+        t_single = time.perf_counter() - t0
+        ok = bool(np.array_equal(u.view(np.uint32), u1.view(np.uint32)) and np.array_equal(v.view(np.uint32), v1.view(np.uint32)))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"world": world, "shape": [args.height, args.width], "levels": args.levels, "iters": args.iters,
+                          "mode": args.mode, "bit_equal_to_single_gpu": ok, "rowband_s": min(times),
+                          "single_gpu_host_call_s": t_single}))
+        assert ok
+
+
+if __name__ == "__main__":
+    main()

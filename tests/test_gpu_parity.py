@@ -346,3 +346,70 @@ def test_error_behaviour(ofb):
         ofb.lk_pyramidal(z, z, num_levels=6)  # 16 -> 8 -> 4 -> 2 -> 1 -> 0
     u, v = ofb.lk_single_scale(np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32), 5)
     assert u.shape == (3, 3) and not u.any()  # smaller than the window: all border
+
+
+# ---------------------------------------------------------------------------------------
+# row-band pyramidal mode (multi-GPU decomposition), emulated with thread ranks on one GPU
+# ---------------------------------------------------------------------------------------
+def _rowband_thread(rank, comm, out, args):
+    import distributed as ofd
+
+    p, c, levels, iters, mode = args
+    try:
+        out[rank] = ofd.lk_pyramidal_rowbands(p, c, levels, 5, iters, mode=mode, comm=comm.view(rank),
+                                              backend=ofd.CudaBackend())
+    except Exception as e:  # surface the failure in the main thread
+        out[rank] = e
+        comm._barrier.abort()
+
+
+@pytest.mark.parametrize("mode_name", ["exact", "fast"])
+@pytest.mark.parametrize("world", [1, 3])
+def test_pyramidal_rowbands_equal_single_gpu(ofb, world, mode_name):
+    """Each rank computes only its rows (plus the shrinking overlap); the gathered result must
+    equal the whole-frame run bit for bit, in both arithmetic modes."""
+    import threading
+
+    import distributed as ofd
+    import synthetic
+
+    mode = ofb.MODE_EXACT if mode_name == "exact" else ofb.MODE_FAST
+    prev, curr, _ = synthetic.make_pairs_numpy(1, 200, 248, seed=31)
+    p, c = prev[0], np.roll(curr[0], 3, axis=0)  # large enough motion for several iterations
+    u1, v1, (iters_exec, _) = ofb.lk_pyramidal(p, c, 3, 5, 3, mode=mode, return_trace=True)
+    if world == 1:
+        u, v = ofd.lk_pyramidal_rowbands(p, c, 3, 5, 3, mode=mode, comm=ofd.SingleProcessComm(), backend=ofd.CudaBackend())
+        results = [(u, v)]
+    else:
+        comm = ofd.ThreadComm(world)
+        results = [None] * world
+        ts = [threading.Thread(target=_rowband_thread, args=(r, comm, results, (p, c, 3, 3, mode))) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    for r, res in enumerate(results):
+        assert not isinstance(res, Exception), res
+        assert_bit_equal(res[0], u1, f"rank {r} u ({mode_name})")
+        assert_bit_equal(res[1], v1, f"rank {r} v ({mode_name})")
+
+
+def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
+    """of_pyramid_down_f32_dev / of_upsample_flow_f32_dev (row range) against the host calls."""
+    import torch
+
+    g = golden_units
+    dev = torch.device("cuda", 0)
+    src = torch.from_numpy(g["pyr_odd_in"]).to(dev)
+    dst = torch.empty((22, 33), dtype=torch.float32, device=dev)
+    ofb.pyramid_down_dev(src.data_ptr(), dst.data_ptr(), 1, 45, 67, 22, 33)
+    torch.cuda.synchronize()
+    assert_bit_equal(dst.cpu().numpy(), g["pyr_odd_level1"], "pyramid_down_dev")
+    cu, cv = torch.from_numpy(g["up_u"]).to(dev), torch.from_numpy(g["up_v"]).to(dev)
+    u = torch.full((61, 83), float("nan"), dtype=torch.float32, device=dev)
+    v = torch.full((61, 83), float("nan"), dtype=torch.float32, device=dev)
+    ofb.upsample_flow_dev(cu.data_ptr(), cv.data_ptr(), u.data_ptr(), v.data_ptr(), 1, 30, 40, 61, 83, 10, 37)
+    torch.cuda.synchronize()
+    un = u.cpu().numpy()
+    assert_bit_equal(un[10:37], g["up_out_u_61x83"][10:37], "upsample rows")
+    assert np.isnan(un[:10]).all() and np.isnan(un[37:]).all()  # rows outside the range untouched
