@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -144,6 +145,7 @@ struct PyrPlan {
     std::vector<int> h, w;                      // k = 0 finest ... L-1 coarsest
     std::vector<size_t> prev_off, curr_off;      // k >= 1
     std::vector<size_t> au_off, av_off, bu_off, bv_off;  // flow ping-pong (A of k = 0 is the caller's u, v)
+    std::vector<size_t> warped_off;                      // warped current frame (split refinement)
     size_t partial_off = 0, sel_off = 0, done_off = 0, total = 0;
     int max_blocks = 0;
 };
@@ -169,6 +171,7 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
     p.av_off.assign(levels, 0);
     p.bu_off.assign(levels, 0);
     p.bv_off.assign(levels, 0);
+    p.warped_off.assign(levels, 0);
     p.max_blocks = 0;
     for (int k = 0; k < levels; ++k) {
         const size_t bytes = align_up((size_t)batch * p.h[k] * p.w[k] * sizeof(float));
@@ -180,6 +183,7 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
         }
         p.bu_off[k] = off; off += bytes;
         p.bv_off[k] = off; off += bytes;
+        p.warped_off[k] = off; off += bytes;
         const int nb = lk_tile_blocks_per_pair(p.h[k], p.w[k]);
         if (nb > p.max_blocks) p.max_blocks = nb;
     }
@@ -188,6 +192,17 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
     p.done_off = off; off += align_up((size_t)levels * batch * sizeof(int));
     p.total = off;
     return OF_OK;
+}
+
+// fast-mode refinement: "split" = warp kernel + K1 marching kernel (default), "fused" = one
+// kernel that gathers the warped frame itself.  Both are kept; OF_B200_REFINE picks.
+bool refine_split() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OF_B200_REFINE");
+        v = (e && std::string(e) == "fused") ? 0 : 1;
+    }
+    return v == 1;
 }
 
 int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int levels,
@@ -271,7 +286,10 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         const bool fast_level = (mode == OF_MODE_FAST) && lk_refine_supported(ra, window);
         for (int it = 0; it < iterations; ++it) {
             if (fast_level) {
-                OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, stream));
+                if (refine_split())
+                    OF_CUDA(launch_lk_refine_split(ra, F(p.warped_off[k]), batch, &cnt.n, stream));
+                else
+                    OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, stream));
             } else {
                 TileArgs a;
                 memset(&a, 0, sizeof(a));
@@ -637,9 +655,14 @@ int of_upsample_flow_f32_dev(const float* coarse_u, const float* coarse_v, float
     return OF_OK;
 }
 
+static size_t refine_partial_bytes(int batch, int height, int width) {
+    return align_up((size_t)batch * lk_tile_blocks_per_pair(height, width) * 2 * sizeof(double));
+}
+
 size_t of_lk_refine_workspace_bytes(int batch, int height, int width) {
     if (batch < 1 || height < 1 || width < 1) return 0;
-    return align_up((size_t)batch * lk_tile_blocks_per_pair(height, width) * 2 * sizeof(double));
+    // per-block partial sums + one plane for the warped current frame (split refinement)
+    return refine_partial_bytes(batch, height, width) + align_up((size_t)batch * height * width * sizeof(float));
 }
 
 int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow_in_u, const float* flow_in_v,
@@ -679,7 +702,11 @@ int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow
     ra.own_hi = own_hi;
     int blocks;
     if (mode == OF_MODE_FAST && lk_refine_supported(ra, window)) {
-        OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, st));
+        float* warped = reinterpret_cast<float*>(static_cast<char*>(workspace) + refine_partial_bytes(batch, height, width));
+        if (refine_split())
+            OF_CUDA(launch_lk_refine_split(ra, warped, batch, &cnt.n, st));
+        else
+            OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, st));
         blocks = lk_refine_units_per_pair(batch, row_hi - row_lo, width);
     } else {
         TileArgs a;

@@ -15,6 +15,16 @@ struct MarchArgs {
     int H, W;
     int n_strips, n_bands, band_rows;
     long long n_units;
+    // REFINE variant (split refinement iteration): `curr` is the already warped current frame,
+    // the result is flow[out] = flow[in] + d with in = sel[pair] ^ sel_xor, rows [row_lo, row_hi),
+    // and sum|du|, sum|dv| over rows [own_lo, own_hi) go to partial[pair][unit][2].
+    float* flow_u[2];
+    float* flow_v[2];
+    const int* sel;
+    int sel_xor;
+    const int* done;
+    double* partial;
+    int row_lo, row_hi, own_lo, own_hi;
 };
 bool lk_march_supported(int H, int W, int window);
 // force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
@@ -42,6 +52,9 @@ struct RefineArgs {
 bool lk_refine_supported(const RefineArgs& a, int window);
 int lk_refine_units_per_pair(int batch, int rows, int W);
 cudaError_t launch_lk_refine(const RefineArgs& a, int batch, int* launches, cudaStream_t stream);
+// Split form of the same iteration: warp_rows (gather the current frame through the flow into
+// `warped`, rows [row_lo - 3, row_hi + 3)) followed by the K1 marching kernel in REFINE mode.
+cudaError_t launch_lk_refine_split(const RefineArgs& a, float* warped, int batch, int* launches, cudaStream_t stream);
 
 // ---- K1/K3 exact: tile kernel in the reference's operation order (lk_tile.cu) ----------
 enum TileSource { SRC_FRAMES = 0, SRC_WARP = 1, SRC_GRADS = 2 };

@@ -62,6 +62,7 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
 constexpr int PYR_MAX_RADIUS = 16;
 constexpr int PYR_RMAX = 40;  // smoothed rows a CTA may need
 constexpr int PYR_CMAX = 72;  // smoothed columns a CTA may need
+constexpr int PYR_SEG = 6;    // outputs per sliding-window run (R = 36 and C = 66 are multiples)
 
 struct PyrArgs {
     const float* src;
@@ -74,7 +75,12 @@ struct PyrArgs {
 };
 
 __device__ __forceinline__ int reflect_index(int i, int n) {
-    // scipy 'reflect': (d c b a | a b c d | d c b a), any overhang
+    // scipy 'reflect': (d c b a | a b c d | d c b a).  One fold covers -n <= i < 2n (every tile
+    // of a frame taller / wider than the filter radius); the modulo form handles any overhang.
+    if (i >= -n && i < 2 * n) {
+        if (i < 0) i = -1 - i;
+        return i >= n ? 2 * n - 1 - i : i;
+    }
     const int period = 2 * n;
     int m = i % period;
     if (m < 0) m += period;
@@ -97,7 +103,7 @@ __device__ __forceinline__ double gauss_tap_sum(const double* x, const double* w
 template <int RADIUS>
 __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
     extern __shared__ float smem[];
-    constexpr int SEG = 8;
+    constexpr int SEG = PYR_SEG;
     const int H = a.H, W = a.W, r = RADIUS > 0 ? RADIUS : a.radius;
     const float* src = a.src + (size_t)blockIdx.z * H * W;
     float* dst = a.dst + (size_t)blockIdx.z * a.oh * a.ow;
@@ -112,11 +118,15 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
     const int fx_hi = min((int)floor(linspace_coord(j1, a.ow, W, a.step_x)) + 1, W - 1);
     const int R = fy_hi - fy_lo + 1, C = fx_hi - fx_lo + 1;
     const int IW = C + 2 * r, IH = R + 2 * r;
-    const int IWP = IW | 1;  // odd pitch: the axis-1 pass walks rows with lanes on different rows
+    // odd pitches: the axis-1 pass and the resampling walk rows with lanes on different rows /
+    // every other column.  Both intermediate planes are padded by one segment so that the
+    // sliding windows can read past the tile end without a clamp (those outputs are discarded).
+    const int IWP = (IW + SEG) | 1;
+    const int CP = C | 1;
 
-    float* img = smem;            // [IH][IW]    source with reflected halo
-    float* tmp = img + IH * IW;   // [R][IWP]    after the axis-0 pass (float32)
-    float* smo = tmp + R * IWP;   // [R][C]      after the axis-1 pass (float32)
+    float* img = smem;                    // [IH + SEG][IW]  source with reflected halo
+    float* tmp = img + (IH + SEG) * IW;   // [R][IWP]        after the axis-0 pass (float32)
+    float* smo = tmp + R * IWP;           // [R][CP]         after the axis-1 pass (float32)
 
     for (int y = wid; y < IH; y += 8) {
         const float* row = src + (size_t)reflect_index(fy_lo - r + y, H) * W;
@@ -125,20 +135,20 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
     __syncthreads();
 
     if (RADIUS > 0) {
-        double w[2 * (RADIUS > 0 ? RADIUS : 1) + 1];
-#pragma unroll
-        for (int k = 0; k < 2 * RADIUS + 1; ++k) w[k] = a.w[k];
+        constexpr int RR = RADIUS > 0 ? RADIUS : 1;
         // axis 0: item = (row segment, column); consecutive lanes take consecutive columns
         const int nseg_v = (R + SEG - 1) / SEG;
         for (int item = tid; item < nseg_v * IW; item += 256) {
             const int seg = item / IW, cc = item - seg * IW;
             const int r0 = seg * SEG;
-            double x[SEG + 2 * (RADIUS > 0 ? RADIUS : 1)];
+            const float* col = img + r0 * IW + cc;
+            double x[SEG + 2 * RR];
 #pragma unroll
-            for (int k = 0; k < SEG + 2 * RADIUS; ++k) x[k] = (double)img[min(r0 + k, IH - 1) * IW + cc];
+            for (int k = 0; k < SEG + 2 * RR; ++k) x[k] = (double)col[k * IW];
+            float* out = tmp + r0 * IWP + cc;
 #pragma unroll
             for (int k = 0; k < SEG; ++k)
-                if (r0 + k < R) tmp[(r0 + k) * IWP + cc] = (float)gauss_tap_sum<(RADIUS > 0 ? RADIUS : 1)>(x + k, w);
+                if (r0 + k < R) out[k * IWP] = (float)gauss_tap_sum<RR>(x + k, a.w);
         }
         __syncthreads();
         // axis 1: item = (column segment, row); consecutive lanes take consecutive rows
@@ -146,12 +156,14 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
         for (int item = tid; item < nseg_h * R; item += 256) {
             const int seg = item / R, rr = item - seg * R;
             const int c0 = seg * SEG;
-            double x[SEG + 2 * (RADIUS > 0 ? RADIUS : 1)];
+            const float* row = tmp + rr * IWP + c0;
+            double x[SEG + 2 * RR];
 #pragma unroll
-            for (int k = 0; k < SEG + 2 * RADIUS; ++k) x[k] = (double)tmp[rr * IWP + min(c0 + k, IW - 1)];
+            for (int k = 0; k < SEG + 2 * RR; ++k) x[k] = (double)row[k];
+            float* out = smo + rr * CP + c0;
 #pragma unroll
             for (int k = 0; k < SEG; ++k)
-                if (c0 + k < C) smo[rr * C + c0 + k] = (float)gauss_tap_sum<(RADIUS > 0 ? RADIUS : 1)>(x + k, w);
+                if (c0 + k < C) out[k] = (float)gauss_tap_sum<RR>(x + k, a.w);
         }
     } else {
         for (int i = tid; i < R * IW; i += 256) {
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
             double acc = dmul((double)row[0], a.w[r]);
             for (int ii = -r; ii < 0; ++ii)
                 acc = dadd(acc, dmul(dadd((double)row[ii], (double)row[-ii]), a.w[ii + r]));
-            smo[i] = (float)acc;
+            smo[rr * CP + cc] = (float)acc;
         }
     }
     __syncthreads();
@@ -184,8 +196,8 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
         // the tap beyond the last row/column has weight exactly 0 (SciPy mirrors its index)
         const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
         const double wy0 = dsub(1.0, fy), wx0 = dsub(1.0, fx);
-        const float* s0 = smo + (y0 - fy_lo) * C - fx_lo;
-        const float* s1 = smo + (y1 - fy_lo) * C - fx_lo;
+        const float* s0 = smo + (y0 - fy_lo) * CP - fx_lo;
+        const float* s1 = smo + (y1 - fy_lo) * CP - fx_lo;
         double t = 0.0;
         t = dadd(t, dmul(dmul((double)s0[x0], wy0), wx0));
         t = dadd(t, dmul(dmul((double)s0[x1], wy0), fx));
@@ -221,7 +233,8 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
     if (a.tile_h > 16) a.tile_h = 16;
     if (a.tile_w > 32) a.tile_w = 32;
     const int IHmax = PYR_RMAX + 2 * radius, IWmax = PYR_CMAX + 2 * radius;
-    const size_t smem = (size_t)(IHmax * IWmax + PYR_RMAX * (IWmax + 1) + PYR_RMAX * PYR_CMAX) * sizeof(float);
+    const size_t smem =
+        (size_t)((IHmax + PYR_SEG) * IWmax + PYR_RMAX * (IWmax + PYR_SEG + 1) + PYR_RMAX * (PYR_CMAX + 1)) * sizeof(float);
     static size_t attr_smem[2] = {0, 0};
     const int which = radius == 8 ? 1 : 0;
     if (smem > attr_smem[which]) {

@@ -241,6 +241,8 @@ class CudaBackend:
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def from_host(self, a):
+        if isinstance(a, self.torch.Tensor):  # already device-resident
+            return a.to(device=self.device, dtype=self.torch.float32).contiguous()
         return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
 
     def to_host(self, t):
@@ -289,10 +291,13 @@ def lk_pyramidal_rowbands(
     comm=None,
     backend=None,
     trace: Optional[list] = None,
+    to_host: bool = True,
 ):
     """Pyramidal LK of ONE [H, W] frame pair with the rows of every level split over the ranks.
-    Every rank returns the full (u, v).  Results equal the single-GPU path bit for bit (same
-    kernels, same row pairing); the early-exit decision uses the all-reduced residual sums."""
+    Every rank returns the full (u, v) -- NumPy arrays, or the backend's device arrays with
+    to_host=False (frames may be passed as device arrays too).  Results equal the single-GPU
+    path bit for bit (same kernels, same row pairing); the early-exit decision uses the
+    all-reduced residual sums."""
     if comm is None:
         comm = TorchDistComm() if _dist() is not None else SingleProcessComm()
     if backend is None:
@@ -349,4 +354,6 @@ def lk_pyramidal_rowbands(
             counts = [shard_range(h, r, world)[1] - shard_range(h, r, world)[0] for r in range(world)]
             flow_u = comm.all_gather_rows(flow_u[a:b].contiguous(), counts)
             flow_v = comm.all_gather_rows(flow_v[a:b].contiguous(), counts)
+    if not to_host:
+        return flow_u, flow_v
     return backend.to_host(flow_u), backend.to_host(flow_v)
