@@ -129,7 +129,7 @@ int of_lk_pyramidal_f32_dev(const float* prev, const float* curr, float* u, floa
 /* one coarser pyramid level for a batch (device version of of_pyramid_down_f32) */
 int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height, int width,
                             int out_height, int out_width, const double* weights, int radius,
-                            void* stream);
+                            int row_lo, int row_hi /* output rows to produce */, void* stream);
 
 /* upsample_flow for target rows [row_lo, row_hi) only */
 int of_upsample_flow_f32_dev(const float* coarse_u, const float* coarse_v, float* u, float* v,
@@ -149,6 +149,21 @@ int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow
                          int height, int width, int window, int mode, int row_lo, int row_hi,
                          int own_lo, int own_hi, double* sums, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* Same iteration with device-side control, so that a rank never waits for the host inside a
+ * level: the flow lives in two ping-pong buffer pairs, sel[pair] (0 / 1) says which one is
+ * current, pairs with done[pair] != 0 are skipped.  After the ranks have all-reduced `sums`,
+ * of_lk_convergence_update_dev applies the reference's test (mean|du| < 0.01 and mean|dv| <
+ * 0.01 over n_pixels), flips sel, sets done and records the trace (optional arrays:
+ * iters_executed[batch], residuals[batch][max_iterations][2]). */
+int of_lk_refine_pingpong_f32_dev(const float* prev, const float* curr, float* flow0_u, float* flow0_v,
+                                  float* flow1_u, float* flow1_v, const int* sel, const int* done,
+                                  int batch, int height, int width, int window, int mode, int row_lo,
+                                  int row_hi, int own_lo, int own_hi, double* sums, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+int of_lk_convergence_update_dev(const double* sums, int batch, double n_pixels, int* sel, int* done,
+                                 int* iters_executed, float* residuals, int max_iterations,
+                                 int iteration, void* stream);
 
 int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
                               int batch, int height, int width, int flags, void* stream);

@@ -291,6 +291,30 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restr
     }
 }
 
+__global__ void convergence_update_kernel(const double* __restrict__ sums, int batch, double n_pixels, int* sel,
+                                          int* done, int* iters_executed, float* residuals, int max_iters,
+                                          int iteration) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= batch || done[pair]) return;
+    const float mu = (float)(sums[2 * pair] / n_pixels), mv = (float)(sums[2 * pair + 1] / n_pixels);
+    sel[pair] ^= 1;
+    if (iters_executed) iters_executed[pair] += 1;
+    if (residuals) {
+        residuals[((size_t)pair * max_iters + iteration) * 2 + 0] = mu;
+        residuals[((size_t)pair * max_iters + iteration) * 2 + 1] = mv;
+    }
+    if (mu < OF_CONVERGENCE_EPS && mv < OF_CONVERGENCE_EPS) done[pair] = 1;
+}
+
+cudaError_t launch_convergence_update(const double* sums, int batch, double n_pixels, int* sel, int* done,
+                                      int* iters_executed, float* residuals, int max_iters, int iteration,
+                                      int* launches, cudaStream_t stream) {
+    if (launches) *launches += 1;
+    convergence_update_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(sums, batch, n_pixels, sel, done, iters_executed,
+                                                                       residuals, max_iters, iteration);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sum_partials(const double* partial, int blocks_per_pair, double* sums, int batch, int* launches,
                                 cudaStream_t stream) {
     if (launches) *launches += 1;

@@ -233,9 +233,9 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
     lc[0] = curr;
     for (int k = 1; k < levels; ++k) {
         OF_CUDA(launch_pyramid_down(lp[k - 1], F(p.prev_off[k]), batch, p.h[k - 1], p.w[k - 1], p.h[k], p.w[k], gw,
-                                    radius, &cnt.n, stream));
+                                    radius, 0, p.h[k], &cnt.n, stream));
         OF_CUDA(launch_pyramid_down(lc[k - 1], F(p.curr_off[k]), batch, p.h[k - 1], p.w[k - 1], p.h[k], p.w[k], gw,
-                                    radius, &cnt.n, stream));
+                                    radius, 0, p.h[k], &cnt.n, stream));
         lp[k] = F(p.prev_off[k]);
         lc[k] = F(p.curr_off[k]);
     }
@@ -495,7 +495,8 @@ int of_pyramid_down_f32(const float* src, float* dst, int height, int width, int
     OF_TRY(g_arena.get(1, ob, reinterpret_cast<void**>(&dd)));
     cudaStream_t st = g_streams[0];
     OF_CUDA(cudaMemcpyAsync(ds, src, ib, cudaMemcpyHostToDevice, st));
-    OF_CUDA(launch_pyramid_down(ds, dd, 1, height, width, out_height, out_width, weights, radius, &cnt.n, st));
+    OF_CUDA(launch_pyramid_down(ds, dd, 1, height, width, out_height, out_width, weights, radius, 0, out_height, &cnt.n,
+                                st));
     OF_CUDA(cudaMemcpyAsync(dst, dd, ob, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaStreamSynchronize(st));
     return OF_OK;
@@ -626,7 +627,7 @@ int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v
 }
 
 int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height, int width, int out_height,
-                            int out_width, const double* weights, int radius, void* stream) {
+                            int out_width, const double* weights, int radius, int row_lo, int row_hi, void* stream) {
     OF_TRY(check_frame(src, dst, height, width));
     if (out_height < 1 || out_width < 1) return fail(OF_ERR_INVALID_ARGUMENT, "output size must be >= 1");
     if (!weights || radius < 0 || radius > OF_MAX_GAUSS_RADIUS)
@@ -634,8 +635,9 @@ int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height,
     if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
     OF_TRY(need_device());
     Counter cnt;
-    OF_CUDA(launch_pyramid_down(src, dst, batch, height, width, out_height, out_width, weights, radius, &cnt.n,
-                                static_cast<cudaStream_t>(stream)));
+    if (row_lo < 0 || row_hi > out_height || row_lo >= row_hi) return fail(OF_ERR_INVALID_ARGUMENT, "bad output row range");
+    OF_CUDA(launch_pyramid_down(src, dst, batch, height, width, out_height, out_width, weights, radius, row_lo, row_hi,
+                                &cnt.n, static_cast<cudaStream_t>(stream)));
     return OF_OK;
 }
 
@@ -665,10 +667,43 @@ size_t of_lk_refine_workspace_bytes(int batch, int height, int width) {
     return refine_partial_bytes(batch, height, width) + align_up((size_t)batch * height * width * sizeof(float));
 }
 
+static int refine_dev_impl(const float* prev, const float* curr, float* flow0_u, float* flow0_v, float* flow1_u,
+                           float* flow1_v, const int* sel, const int* done, int batch, int height, int width, int window,
+                           int mode, int row_lo, int row_hi, int own_lo, int own_hi, double* sums, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow_in_u, const float* flow_in_v,
                          float* flow_out_u, float* flow_out_v, int batch, int height, int width, int window, int mode,
                          int row_lo, int row_hi, int own_lo, int own_hi, double* sums, void* workspace,
                          size_t workspace_bytes, void* stream) {
+    return refine_dev_impl(prev, curr, const_cast<float*>(flow_in_u), const_cast<float*>(flow_in_v), flow_out_u,
+                           flow_out_v, nullptr, nullptr, batch, height, width, window, mode, row_lo, row_hi, own_lo,
+                           own_hi, sums, workspace, workspace_bytes, stream);
+}
+
+int of_lk_refine_pingpong_f32_dev(const float* prev, const float* curr, float* flow0_u, float* flow0_v, float* flow1_u,
+                                  float* flow1_v, const int* sel, const int* done, int batch, int height, int width,
+                                  int window, int mode, int row_lo, int row_hi, int own_lo, int own_hi, double* sums,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    if (!sel || !done) return fail(OF_ERR_INVALID_ARGUMENT, "sel / done missing");
+    return refine_dev_impl(prev, curr, flow0_u, flow0_v, flow1_u, flow1_v, sel, done, batch, height, width, window, mode,
+                           row_lo, row_hi, own_lo, own_hi, sums, workspace, workspace_bytes, stream);
+}
+
+int of_lk_convergence_update_dev(const double* sums, int batch, double n_pixels, int* sel, int* done,
+                                 int* iters_executed, float* residuals, int max_iterations, int iteration, void* stream) {
+    if (!sums || !sel || !done || batch < 1 || n_pixels <= 0) return fail(OF_ERR_INVALID_ARGUMENT, "bad argument");
+    OF_TRY(need_device());
+    Counter cnt;
+    OF_CUDA(launch_convergence_update(sums, batch, n_pixels, sel, done, iters_executed, residuals, max_iterations,
+                                      iteration, &cnt.n, static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+static int refine_dev_impl(const float* prev, const float* curr, float* flow_in_u, float* flow_in_v, float* flow_out_u,
+                           float* flow_out_v, const int* sel, const int* done, int batch, int height, int width, int window,
+                           int mode, int row_lo, int row_hi, int own_lo, int own_hi, double* sums, void* workspace,
+                           size_t workspace_bytes, void* stream) {
     OF_TRY(check_frame(prev, curr, height, width));
     OF_TRY(check_frame(flow_in_u, flow_in_v, height, width));
     OF_TRY(check_frame(flow_out_u, flow_out_v, height, width));
@@ -689,10 +724,12 @@ int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow
     memset(&ra, 0, sizeof(ra));
     ra.prev = prev;
     ra.curr = curr;
-    ra.flow_u[0] = const_cast<float*>(flow_in_u);
-    ra.flow_v[0] = const_cast<float*>(flow_in_v);
+    ra.flow_u[0] = flow_in_u;
+    ra.flow_v[0] = flow_in_v;
     ra.flow_u[1] = flow_out_u;
     ra.flow_v[1] = flow_out_v;
+    ra.sel = sel;
+    ra.done = done;
     ra.partial = partial;
     ra.H = height;
     ra.W = width;
@@ -717,6 +754,8 @@ int of_lk_refine_f32_dev(const float* prev, const float* curr, const float* flow
         a.flow_v[0] = ra.flow_v[0];
         a.flow_u[1] = flow_out_u;
         a.flow_v[1] = flow_out_v;
+        a.sel = sel;
+        a.done = done;
         a.partial = partial;
         a.H = height;
         a.W = width;

@@ -98,6 +98,10 @@ struct IterFinalizeArgs {
 cudaError_t launch_iter_finalize(const IterFinalizeArgs& a, int batch, int* launches, cudaStream_t stream);
 // row-band mode: just the per-pair sums (sum|du|, sum|dv| over this rank's rows) -> sums[pair][2];
 // the ranks all-reduce them and take the decision on the host side of the C ABI
+// the same decision as iter_finalize, from sums that were already reduced (over blocks and ranks)
+cudaError_t launch_convergence_update(const double* sums, int batch, double n_pixels, int* sel, int* done,
+                                      int* iters_executed, float* residuals, int max_iters, int iteration,
+                                      int* launches, cudaStream_t stream);
 cudaError_t launch_sum_partials(const double* partial, int blocks_per_pair, double* sums, int batch, int* launches,
                                 cudaStream_t stream);
 
@@ -107,7 +111,8 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
 // fused Gaussian (separable, float64 accumulate, float32 store per axis, reflect) + bilinear
 // resample on the np.linspace grid (lucas_kanade_pyramidal.py:44-59)
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
-                                const double* weights, int radius, int* launches, cudaStream_t stream);
+                                const double* weights, int radius, int row_lo, int row_hi, int* launches,
+                                cudaStream_t stream);
 cudaError_t launch_warp(const float* img, const float* fu, const float* fv, float* out, int batch, int H, int W,
                         int* launches, cudaStream_t stream);
 // coarse flow (selected ping-pong buffer) -> fine grid, scaled (lucas_kanade_pyramidal.py:100-138)

@@ -69,6 +69,7 @@ struct PyrArgs {
     float* dst;
     int H, W, oh, ow;
     int tile_h, tile_w;  // coarse pixels per CTA
+    int row_lo, row_hi;  // coarse rows to produce
     int radius;
     double step_y, step_x;
     double w[2 * PYR_MAX_RADIUS + 1];
@@ -109,8 +110,8 @@ __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
     float* dst = a.dst + (size_t)blockIdx.z * a.oh * a.ow;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    const int i0 = blockIdx.y * a.tile_h, j0 = blockIdx.x * a.tile_w;
-    const int i1 = min(i0 + a.tile_h, a.oh) - 1, j1 = min(j0 + a.tile_w, a.ow) - 1;
+    const int i0 = a.row_lo + blockIdx.y * a.tile_h, j0 = blockIdx.x * a.tile_w;
+    const int i1 = min(i0 + a.tile_h, a.row_hi) - 1, j1 = min(j0 + a.tile_w, a.ow) - 1;
     // fine rows / columns whose smoothed value the bilinear taps of this tile can touch
     const int fy_lo = (int)floor(linspace_coord(i0, a.oh, H, a.step_y));
     const int fy_hi = min((int)floor(linspace_coord(i1, a.oh, H, a.step_y)) + 1, H - 1);
@@ -215,8 +216,10 @@ static int pyr_tile_extent(int limit, double step) {
 }
 
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
-                                const double* weights, int radius, int* launches, cudaStream_t stream) {
+                                const double* weights, int radius, int row_lo, int row_hi, int* launches,
+                                cudaStream_t stream) {
     if (radius < 0 || radius > PYR_MAX_RADIUS || oh < 1 || ow < 1 || batch > 65535) return cudaErrorInvalidValue;
+    if (row_lo < 0 || row_hi > oh || row_lo >= row_hi) return cudaErrorInvalidValue;
     PyrArgs a;
     a.src = src;
     a.dst = dst;
@@ -225,6 +228,8 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
     a.oh = oh;
     a.ow = ow;
     a.radius = radius;
+    a.row_lo = row_lo;
+    a.row_hi = row_hi;
     a.step_y = oh > 1 ? (double)(H - 1) / (double)(oh - 1) : 0.0;  // np.linspace step
     a.step_x = ow > 1 ? (double)(W - 1) / (double)(ow - 1) : 0.0;
     for (int i = 0; i < 2 * radius + 1; ++i) a.w[i] = weights[i];
@@ -244,7 +249,7 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
         attr_smem[which] = smem;
     }
     if (launches) *launches += 1;
-    dim3 grid((ow + a.tile_w - 1) / a.tile_w, (oh + a.tile_h - 1) / a.tile_h, batch);
+    dim3 grid((ow + a.tile_w - 1) / a.tile_w, (row_hi - row_lo + a.tile_h - 1) / a.tile_h, batch);
     if (which)
         pyramid_down_kernel<8><<<grid, 256, smem, stream>>>(a);  // sigma = 2, the reference's pyramid
     else

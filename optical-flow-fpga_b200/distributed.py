@@ -254,11 +254,42 @@ class CudaBackend:
     def zeros(self, h, w):
         return self.torch.zeros((h, w), dtype=self.torch.float32, device=self.device)
 
-    def pyramid_down(self, img):
+    def pyramid_down(self, img, lo=0, hi=None):
+        """Rows [lo, hi) of the next coarser level (the other rows of the result are undefined)."""
         h, w = img.shape
         out = self.empty(int(h * 0.5), int(w * 0.5))
-        self.ofb.pyramid_down_dev(img.data_ptr(), out.data_ptr(), 1, h, w, out.shape[0], out.shape[1], self._stream())
+        self.ofb.pyramid_down_dev(img.data_ptr(), out.data_ptr(), 1, h, w, out.shape[0], out.shape[1], self._stream(),
+                                  2.0, lo, out.shape[0] if hi is None else hi)
         return out
+
+    # ---- device-side iteration control (no host round trip inside a level) ----------------
+    def int_zeros(self, n):
+        return self.torch.zeros(n, dtype=self.torch.int32, device=self.device)
+
+    def f32_zeros(self, n):
+        return self.torch.zeros(n, dtype=self.torch.float32, device=self.device)
+
+    def refine_pingpong(self, prev, curr, f0u, f0v, f1u, f1v, sel, done, window, mode, lo, hi, own_lo, own_hi):
+        h, w = prev.shape
+        need = self.ofb.lk_refine_workspace_bytes(1, h, w)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        sums = self.torch.zeros(2, dtype=self.torch.float64, device=self.device)
+        self.ofb.lk_refine_pingpong_dev(prev.data_ptr(), curr.data_ptr(), f0u.data_ptr(), f0v.data_ptr(), f1u.data_ptr(),
+                                        f1v.data_ptr(), sel.data_ptr(), done.data_ptr(), 1, h, w, window, mode, lo, hi,
+                                        own_lo, own_hi, sums.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                        self._stream())
+        return sums
+
+    def select_rows(self, sel, buf0, buf1, r0, r1):
+        """Plane whose rows [r0, r1) are those of buf1 if sel != 0 else buf0 (no host read)."""
+        out = buf0 if (r0, r1) == (0, buf0.shape[0]) else self.torch.empty_like(buf0)
+        out[r0:r1] = self.torch.where(sel[0] > 0, buf1[r0:r1], buf0[r0:r1])
+        return out
+
+    def convergence_update(self, sums, n_pixels, sel, done, iters_t, resid_t, max_iters, it):
+        self.ofb.lk_convergence_update_dev(sums.data_ptr(), 1, n_pixels, sel.data_ptr(), done.data_ptr(),
+                                           iters_t.data_ptr(), resid_t.data_ptr(), max_iters, it, self._stream())
 
     def upsample(self, cu, cv, th, tw, lo, hi):
         u, v = self.empty(th, tw), self.empty(th, tw)
@@ -312,12 +343,30 @@ def lk_pyramidal_rowbands(
         raise ValueError("row-band mode supports window_size <= 5")
     iters = int(num_iterations)
 
+    def gather(arr, h):
+        """Full plane from the ranks' owned rows (every rank computed rows shard_range(h) only)."""
+        if world == 1:
+            return arr
+        a_, b_ = shard_range(h, rank, world)
+        counts = [shard_range(h, r, world)[1] - shard_range(h, r, world)[0] for r in range(world)]
+        return comm.all_gather_rows(arr[a_:b_].contiguous(), counts)
+
+    # Gaussian pyramids: every rank smooths / decimates its rows of each level, then the level
+    # is all-gathered (the next level's filter and the warp gather reach into other bands)
     lv_prev = [backend.from_host(frame_prev)]
     lv_curr = [backend.from_host(frame_curr)]
     for _ in range(1, int(num_levels)):
-        lv_prev.insert(0, backend.pyramid_down(lv_prev[0]))
-        lv_curr.insert(0, backend.pyramid_down(lv_curr[0]))
+        oh = int(lv_prev[0].shape[0] * 0.5)
+        a, b = shard_range(oh, rank, world)
+        if b > a:
+            nxt_p, nxt_c = backend.pyramid_down(lv_prev[0], a, b), backend.pyramid_down(lv_curr[0], a, b)
+        else:
+            nxt_p = nxt_c = backend.empty(oh, int(lv_prev[0].shape[1] * 0.5))
+        lv_prev.insert(0, gather(nxt_p, oh))
+        lv_curr.insert(0, gather(nxt_c, oh))
 
+    device_control = hasattr(backend, "refine_pingpong")
+    want_trace_sync = trace is not None
     h, w = lv_prev[0].shape
     flow_u, flow_v = backend.zeros(h, w), backend.zeros(h, w)
     for level, (img_prev, img_curr) in enumerate(zip(lv_prev, lv_curr)):
@@ -331,29 +380,60 @@ def lk_pyramidal_rowbands(
             else:
                 flow_u, flow_v = backend.empty(h, w), backend.empty(h, w)
         out_u, out_v = backend.empty(h, w), backend.empty(h, w)
-        for it in range(iters):
+        n = float(h) * float(w)
+
+        def rows_of(it):
             ext = GROW * (iters - 1 - it)
-            lo = max(0, a - ext)
-            lo -= lo & 1  # even: rows pair up identically on every rank
-            hi = min(h, b + ext)
-            if b > a:
-                sums = backend.refine(img_prev, img_curr, flow_u, flow_v, out_u, out_v, window_size, mode, lo, hi, a, b)
-            else:
-                sums = backend.zero_sums()
-            sums = comm.all_reduce_sum(sums)
-            s = sums.detach().cpu().numpy() if hasattr(sums, "detach") else np.asarray(sums)
-            n = float(h) * float(w)
-            mean_du, mean_dv = np.float32(s[0] / n), np.float32(s[1] / n)
+            lo_ = max(0, a - ext)
+            return lo_ - (lo_ & 1), min(h, b + ext)  # even start: rows pair up identically on every rank
+
+        if device_control:
+            # all iterations are enqueued back to back; the convergence test, the ping-pong flip
+            # and the skipping of iterations after convergence happen on the device
+            sel, done, iters_t = backend.int_zeros(1), backend.int_zeros(1), backend.int_zeros(1)
+            resid_t = backend.f32_zeros(2 * max(iters, 1))
+            for it in range(iters):
+                lo, hi = rows_of(it)
+                if b > a:
+                    sums = backend.refine_pingpong(img_prev, img_curr, flow_u, flow_v, out_u, out_v, sel, done,
+                                                   window_size, mode, lo, hi, a, b)
+                else:
+                    sums = backend.zero_sums()
+                sums = comm.all_reduce_sum(sums)
+                backend.convergence_update(sums, n, sel, done, iters_t, resid_t, iters, it)
+            if iters > 0:
+                if hasattr(backend, "select_rows") and not want_trace_sync:
+                    # pick the current ping-pong buffer on the device (owned rows only when they
+                    # are gathered afterwards): the whole call never waits for the GPU, so it
+                    # can be captured in a CUDA graph
+                    r0, r1 = (a, b) if world > 1 else (0, h)
+                    flow_u = backend.select_rows(sel, flow_u, out_u, r0, r1)
+                    flow_v = backend.select_rows(sel, flow_v, out_v, r0, r1)
+                elif int(sel.cpu()[0]) == 1:  # one host read per level
+                    flow_u, flow_v = out_u, out_v
             if trace is not None:
-                trace.append((level, it, float(mean_du), float(mean_dv)))
-            flow_u, out_u = out_u, flow_u
-            flow_v, out_v = out_v, flow_v
-            if mean_du < np.float32(0.01) and mean_dv < np.float32(0.01):
-                break
-        if world > 1:
-            counts = [shard_range(h, r, world)[1] - shard_range(h, r, world)[0] for r in range(world)]
-            flow_u = comm.all_gather_rows(flow_u[a:b].contiguous(), counts)
-            flow_v = comm.all_gather_rows(flow_v[a:b].contiguous(), counts)
+                res = resid_t.cpu().numpy()
+                for it in range(int(iters_t.cpu()[0])):
+                    trace.append((level, it, float(res[2 * it]), float(res[2 * it + 1])))
+        else:
+            for it in range(iters):
+                lo, hi = rows_of(it)
+                if b > a:
+                    sums = backend.refine(img_prev, img_curr, flow_u, flow_v, out_u, out_v, window_size, mode, lo, hi, a, b)
+                else:
+                    sums = backend.zero_sums()
+                sums = comm.all_reduce_sum(sums)
+                s = sums.detach().cpu().numpy() if hasattr(sums, "detach") else np.asarray(sums)
+                mean_du, mean_dv = np.float32(s[0] / n), np.float32(s[1] / n)
+                if trace is not None:
+                    trace.append((level, it, float(mean_du), float(mean_dv)))
+                flow_u, out_u = out_u, flow_u
+                flow_v, out_v = out_v, flow_v
+                if mean_du < np.float32(0.01) and mean_dv < np.float32(0.01):
+                    break
+        # level done: rows [a, b) are final on this rank -> every rank gets the whole plane
+        flow_u, flow_v = gather(flow_u, h), gather(flow_v, h)
     if not to_host:
         return flow_u, flow_v
     return backend.to_host(flow_u), backend.to_host(flow_v)
+

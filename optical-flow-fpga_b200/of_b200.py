@@ -71,7 +71,12 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, C.c_size_t, _vp, _vp, _vp],
     ),
     "of_lk_single_scale_fx_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "of_pyramid_down_f32_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "of_pyramid_down_f32_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "of_lk_refine_pingpong_f32_dev": (
+        _i,
+        [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp],
+    ),
+    "of_lk_convergence_update_dev": (_i, [_vp, _i, C.c_double, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "of_upsample_flow_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "of_lk_refine_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "of_lk_refine_f32_dev": (
@@ -350,11 +355,34 @@ def lk_pyramidal_dev(
     )
 
 
-def pyramid_down_dev(src_ptr, dst_ptr, batch, height, width, out_height, out_width, stream=0, sigma: float = 2.0):
+def pyramid_down_dev(src_ptr, dst_ptr, batch, height, width, out_height, out_width, stream=0, sigma: float = 2.0,
+                     row_lo: int = 0, row_hi: Optional[int] = None):
     wts = gaussian_weights(sigma)
     _check(
         lib().of_pyramid_down_f32_dev(
-            src_ptr, dst_ptr, batch, height, width, out_height, out_width, _ptr(wts), (len(wts) - 1) // 2, stream
+            src_ptr, dst_ptr, batch, height, width, out_height, out_width, _ptr(wts), (len(wts) - 1) // 2,
+            row_lo, out_height if row_hi is None else row_hi, stream,
+        )
+    )
+
+
+def lk_refine_pingpong_dev(
+    prev_ptr, curr_ptr, f0u, f0v, f1u, f1v, sel_ptr, done_ptr, batch, height, width, window_size, mode,
+    row_lo, row_hi, own_lo, own_hi, sums_ptr, workspace_ptr, workspace_bytes, stream=0,
+):
+    _check(
+        lib().of_lk_refine_pingpong_f32_dev(
+            prev_ptr, curr_ptr, f0u, f0v, f1u, f1v, sel_ptr, done_ptr, batch, height, width, _window(window_size), mode,
+            row_lo, row_hi, own_lo, own_hi, sums_ptr, workspace_ptr, workspace_bytes, stream,
+        )
+    )
+
+
+def lk_convergence_update_dev(sums_ptr, batch, n_pixels, sel_ptr, done_ptr, iters_ptr, resid_ptr, max_iterations,
+                              iteration, stream=0):
+    _check(
+        lib().of_lk_convergence_update_dev(
+            sums_ptr, batch, float(n_pixels), sel_ptr, done_ptr, iters_ptr, resid_ptr, max_iterations, iteration, stream
         )
     )
 

@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--mode", choices=["exact", "fast"], default="fast")
     ap.add_argument("--repeat", type=int, default=3)
     args = ap.parse_args()
+    import faulthandler
+
+    faulthandler.dump_traceback_later(60, exit=True)  # a wedged job must not hold the GPUs
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     of_b200.set_device(local)
@@ -76,6 +79,7 @@ def main():
         t_single = min(ts[1:])
         u1, v1 = u1d.cpu().numpy(), v1d.cpu().numpy()
         ok = bool(np.array_equal(u.view(np.uint32), u1.view(np.uint32)) and np.array_equal(v.view(np.uint32), v1.view(np.uint32)))
+    faulthandler.cancel_dump_traceback_later()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -121,10 +121,14 @@ class OracleBackend:
     def zero_sums(self):
         return self.torch.zeros(2, dtype=self.torch.float64)
 
-    def pyramid_down(self, img):
+    def pyramid_down(self, img, lo=0, hi=None):
         from oracle import lk_float_oracle as orc
 
-        return self.torch.from_numpy(orc.build_gaussian_pyramid(img.numpy(), 2)[0].copy())
+        full = orc.build_gaussian_pyramid(img.numpy(), 2)[0]
+        out = self.empty(*full.shape)
+        hi = full.shape[0] if hi is None else hi
+        out[lo:hi] = self.torch.from_numpy(full[lo:hi].copy())
+        return out
 
     def upsample(self, cu, cv, th, tw, lo, hi):
         from oracle import lk_float_oracle as orc
