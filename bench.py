@@ -39,6 +39,9 @@ WORKLOADS = {
     # name: (batch per GPU, H, W, pyramidal?, levels, iterations)
     "single_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1),
     "pyramidal_4k": dict(batch=16, H=2160, W=3840, pyramidal=True, levels=3, iters=3),
+    # BASELINE config 5: few very large frames; with N > 1 GPUs every pair is split into row
+    # bands over all ranks (strong scaling, NCCL all-reduce per iteration + all-gather per level)
+    "pyramidal_8k": dict(batch=2, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True),
 }
 WINDOW = 5
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
@@ -261,8 +264,67 @@ def workload_config(name: str, wl: dict) -> dict:
         "width": wl["W"],
         "window": WINDOW,
         "l2": "per-step inputs + outputs are far larger than the 126 MB L2, so no flush between iterations",
-        "parallelism": "independent frame pairs sharded by rank, no data-path collective",
+        "parallelism": ("each pair split into row bands over all ranks: all-reduce of the residual sums per "
+                        "iteration, all-gather of the owned rows per level (NCCL)") if wl.get("rowband")
+        else "independent frame pairs sharded by rank, no data-path collective",
     }
+
+
+def measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier):
+    """Same metric through the host-buffer C-ABI call (of_lk_single_scale_f32): every step copies
+    the step's frames from pinned host memory to the device, runs the kernel and copies (u, v)
+    back, inside the timed region.  If the host cannot pin four full batches, the e2e batch is
+    halved until it fits (said in the result)."""
+    B, H, W = wl["batch"], wl["H"], wl["W"]
+    eb = B
+    bufs = None
+    while eb >= 1:
+        try:
+            bufs = [of_b200.PinnedArray((eb, H, W)) for _ in range(4)]
+            break
+        except Exception:
+            bufs = None
+            eb //= 2
+    ok_all = torch.tensor([1 if bufs is not None else 0, eb], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    if int(ok_all[0].item()) == 0:
+        return {"value": None, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "unavailable": "could not allocate pinned host buffers"}
+    eb = int(ok_all[1].item())  # every rank uses the smallest batch any rank could pin
+    hp, hc, hu, hv = (b.array[:eb] for b in bufs)
+    hp[...] = prev[:eb].cpu().numpy()
+    hc[...] = curr[:eb].cpu().numpy()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):  # warm-up: arena allocation, streams
+        of_b200.lk_single_scale_batch(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        of_b200.lk_single_scale_batch(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item())
+    same = bool(np.array_equal(hu[eb - 1].view(np.uint32), u[eb - 1].cpu().numpy().view(np.uint32)))
+    px = eb * H * W
+    out = {
+        "value": world * px / (e2e_ms * 1e-3) / 1e6,
+        "unit": "Mpixel/s",
+        "h2d_bytes_per_step": 2 * px * 4,
+        "d2h_bytes_per_step": 2 * px * 4,
+        "ms_per_step": e2e_ms,
+        "steps": e2e_steps,
+        "frame_pairs_per_step_per_gpu": eb,
+        "api": "of_lk_single_scale_f32 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams",
+        "matches_device_run": same,
+    }
+    del hp, hc, hu, hv
+    for b in bufs:
+        b.free()
+    return out
 
 
 # ---------------------------------------------------------------------------------------
@@ -285,12 +347,26 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
 
     B, H, W = wl["batch"], wl["H"], wl["W"]
     pixels_per_step = B * H * W
-    prev, curr, _ = synthetic.make_pairs_torch(B, H, W, dev, seed=1234 + rank)
+    rowband = bool(wl.get("rowband")) and world > 1
+    # row-band mode: all ranks work on the SAME pairs (strong scaling); batch mode: own pairs
+    prev, curr, _ = synthetic.make_pairs_torch(B, H, W, dev, seed=1234 + (0 if rowband else rank))
     u = torch.empty_like(prev)
     v = torch.empty_like(prev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    if wl["pyramidal"]:
+    if rowband:
+        import distributed as ofd
+
+        backend = ofd.CudaBackend()
+        comm = ofd.TorchDistComm()
+
+        def step():
+            for b in range(B):
+                ub, vb = ofd.lk_pyramidal_rowbands(prev[b], curr[b], wl["levels"], WINDOW, wl["iters"],
+                                                   mode=of_b200.MODE_FAST, comm=comm, backend=backend, to_host=False)
+                u[b].copy_(ub)
+                v[b].copy_(vb)
+    elif wl["pyramidal"]:
         ws_bytes = of_b200.lk_pyramidal_workspace_bytes(B, H, W, wl["levels"], wl["iters"])
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 
@@ -330,7 +406,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    value = world * pixels_per_step / (ms_per_step * 1e-3) / 1e6  # Mpixel/s, whole job
+    jobs = 1 if rowband else world  # row bands: the ranks share one batch
+    value = jobs * pixels_per_step / (ms_per_step * 1e-3) / 1e6  # Mpixel/s, whole job
 
     # ---- parity of what was just timed (device result vs oracle on sampled pairs) ----------
     parity = None
@@ -343,7 +420,11 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         worst, frac_big, mean_diff = 0.0, 0.0, 0.0
         for b in idx:
             p_h, c_h = prev[b].cpu().numpy(), curr[b].cpu().numpy()
-            if wl["pyramidal"]:
+            if wl["pyramidal"] and H * W > 3840 * 2160:
+                # the NumPy oracle needs minutes at 8K x 50 iterations: use the exact-mode kernels,
+                # which the GPU tests hold bit-identical to the oracle
+                uo, vo = of_b200.lk_pyramidal(p_h, c_h, wl["levels"], WINDOW, wl["iters"], mode=of_b200.MODE_EXACT)
+            elif wl["pyramidal"]:
                 uo, vo = orc.lucas_kanade_pyramidal(p_h, c_h, wl["levels"], WINDOW, wl["iters"])
             else:
                 uo, vo = orc.lucas_kanade_single_scale(p_h, c_h, WINDOW)
@@ -356,6 +437,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             mean_diff = max(mean_diff, float(d.mean()))
         parity = {"bit_exact_vs_oracle": ok, "pairs_checked": len(idx), "max_abs_diff_px": worst,
                   "frac_pixels_diff_gt_1e-3": frac_big, "mean_abs_diff_px": mean_diff}
+        if wl["pyramidal"] and H * W > 3840 * 2160:
+            parity["checked_against"] = "exact-mode GPU path (bit-identical to the oracle in tests/)"
         if wl["pyramidal"]:
             parity["note"] = ("fast mode: warp is the reference's float64 bilinear bit for bit, window sums are "
                               "separable float32 (different association), so ill-conditioned pixels can move")
@@ -363,37 +446,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
     e2e = None
     if not wl["pyramidal"] and not args.no_e2e:
-        hp = of_b200.PinnedArray((B, H, W))
-        hc = of_b200.PinnedArray((B, H, W))
-        hu = of_b200.PinnedArray((B, H, W))
-        hv = of_b200.PinnedArray((B, H, W))
-        hp.array[...] = prev.cpu().numpy()
-        hc.array[...] = curr.cpu().numpy()
-        e2e_steps = max(1, min(args.steps, 5))
-        of_b200.lk_single_scale_batch(hp.array, hc.array, WINDOW, of_b200.MODE_FAST, out=(hu.array, hv.array))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            of_b200.lk_single_scale_batch(hp.array, hc.array, WINDOW, of_b200.MODE_FAST, out=(hu.array, hv.array))
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t2.item())
-        same = bool(np.array_equal(hu.array[B - 1].view(np.uint32), u[B - 1].cpu().numpy().view(np.uint32)))
-        e2e = {
-            "value": world * pixels_per_step / (e2e_ms * 1e-3) / 1e6,
-            "unit": "Mpixel/s",
-            "h2d_bytes_per_step": 2 * pixels_per_step * 4,
-            "d2h_bytes_per_step": 2 * pixels_per_step * 4,
-            "ms_per_step": e2e_ms,
-            "steps": e2e_steps,
-            "api": "of_lk_single_scale_f32 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams",
-            "matches_device_run": same,
-        }
-        for a in (hp, hc, hu, hv):
-            a.free()
+        e2e = measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier)
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -432,12 +485,12 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if rowband else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
         "config": workload_config(args.workload, wl),
-        "frame_pairs_per_s": world * B / (ms_per_step * 1e-3),
+        "frame_pairs_per_s": jobs * B / (ms_per_step * 1e-3),
         "roofline": {
             "bound": "hbm",
             "achieved": achieved,

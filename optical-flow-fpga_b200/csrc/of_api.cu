@@ -112,7 +112,10 @@ int check_window(int window) {
 int single_scale_dev(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int window,
                      int mode, cudaStream_t stream, Counter& cnt) {
     if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
-    if (mode == OF_MODE_FAST && lk_march_supported(H, W, window)) {
+    // the marching kernel moves 128-bit words: all four planes must be 16-byte aligned
+    const bool aligned = ((reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(curr) |
+                           reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (mode == OF_MODE_FAST && aligned && lk_march_supported(H, W, window)) {
         OF_CUDA(launch_lk_march(prev, curr, u, v, batch, H, W, 0, &cnt.n, stream));
         return OF_OK;
     }

@@ -413,3 +413,71 @@ def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
     un = u.cpu().numpy()
     assert_bit_equal(un[10:37], g["up_out_u_61x83"][10:37], "upsample rows")
     assert np.isnan(un[:10]).all() and np.isnan(un[37:]).all()  # rows outside the range untouched
+
+
+# ---------------------------------------------------------------------------------------
+# edge cases of the boundary
+# ---------------------------------------------------------------------------------------
+def test_fast_mode_falls_back_to_reference_order_kernel_on_unaligned_widths(ofb):
+    """Widths that are not a multiple of 4 cannot use TMA / 128-bit loads: fast mode then runs the
+    exact kernel (never a CPU path), so the result is still the reference's."""
+    rng = np.random.default_rng(17)
+    for shape in ((45, 67), (9, 13), (64, 126)):
+        p = (rng.random(shape) * 255).astype(np.float32)
+        c = (p + rng.standard_normal(shape).astype(np.float32)).astype(np.float32)
+        uo, vo = orc.lucas_kanade_single_scale(p, c, 5)
+        u, v = ofb.lk_single_scale(p, c, 5, mode=ofb.MODE_FAST)
+        assert_bit_equal(u, uo, f"{shape} u")
+        assert_bit_equal(v, vo, f"{shape} v")
+
+
+def test_empty_batch_and_tiny_frames(ofb):
+    z = np.zeros((0, 32, 32), np.float32)
+    u, v = ofb.lk_single_scale_batch(z, z, 5, mode=ofb.MODE_FAST)
+    assert u.shape == (0, 32, 32)
+    u, v = ofb.lk_pyramidal_batch(z, z, 2, 5, 2)
+    assert u.shape == (0, 32, 32)
+    for shape in ((1, 1), (1, 8), (8, 1), (5, 5), (6, 8)):
+        p = np.arange(shape[0] * shape[1], dtype=np.float32).reshape(shape)
+        c = p[::-1].copy()
+        for mode in (ofb.MODE_FAST, ofb.MODE_EXACT):
+            u, v = ofb.lk_single_scale(p, c, 5, mode=mode)
+            uo, vo = orc.lucas_kanade_single_scale(p, c, 5)
+            assert_bit_equal(u, uo, f"{shape} mode {mode}")
+            assert_bit_equal(v, vo, f"{shape} mode {mode}")
+
+
+def test_8k_single_scale_locality_and_unaligned_base(ofb):
+    """Largest frame of BASELINE.json (7680x4320): full-frame fast kernel against crops computed
+    on their own (locality), plus planes whose base pointer is not 16-byte aligned (the marching
+    kernel moves 128-bit words, so the driver must route those to the tile kernel)."""
+    import synthetic
+    import torch
+
+    prev, curr, _ = synthetic.make_pairs_numpy(1, 4320, 7680, seed=41)
+    u, v = ofb.lk_single_scale(prev[0], curr[0], 5, mode=ofb.MODE_FAST)
+    for ys, xs in ((slice(0, 300), slice(0, 400)), (slice(4000, 4320), slice(7200, 7680)), (slice(2001, 2301), slice(3333, 3733))):
+        uo, vo = orc.lucas_kanade_single_scale(prev[0][ys, xs], curr[0][ys, xs], 5)
+        h, w = uo.shape
+        # rows / columns that are interior to the crop but not to the frame differ (crop border)
+        y0 = 0 if ys.start == 0 else 3
+        y1 = h if ys.stop == 4320 else h - 3
+        x0 = 0 if xs.start == 0 else 3
+        x1 = w if xs.stop == 7680 else w - 3
+        assert_bit_equal(u[ys, xs][y0:y1, x0:x1], uo[y0:y1, x0:x1], "8K crop u")
+        assert_bit_equal(v[ys, xs][y0:y1, x0:x1], vo[y0:y1, x0:x1], "8K crop v")
+    # device pointers offset by one float
+    dev = torch.device("cuda", 0)
+    h, w = 200, 248
+    buf_p = torch.zeros(h * w + 1, dtype=torch.float32, device=dev)
+    buf_c = torch.zeros(h * w + 1, dtype=torch.float32, device=dev)
+    buf_p[1:] = torch.from_numpy(prev[0][:h, :w].copy()).flatten().to(dev)
+    buf_c[1:] = torch.from_numpy(curr[0][:h, :w].copy()).flatten().to(dev)
+    out_u = torch.empty(h * w, dtype=torch.float32, device=dev)
+    out_v = torch.empty(h * w, dtype=torch.float32, device=dev)
+    ofb.lk_single_scale_dev(buf_p.data_ptr() + 4, buf_c.data_ptr() + 4, out_u.data_ptr(), out_v.data_ptr(), 1, h, w, 5,
+                            ofb.MODE_FAST)
+    torch.cuda.synchronize()
+    uo, vo = orc.lucas_kanade_single_scale(prev[0][:h, :w], curr[0][:h, :w], 5)
+    assert_bit_equal(out_u.cpu().numpy().reshape(h, w), uo, "unaligned base u")
+    assert_bit_equal(out_v.cpu().numpy().reshape(h, w), vo, "unaligned base v")
