@@ -39,6 +39,9 @@ WORKLOADS = {
     # name: (batch per GPU, H, W, pyramidal?, levels, iterations)
     "single_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1),
     "pyramidal_4k": dict(batch=16, H=2160, W=3840, pyramidal=True, levels=3, iters=3),
+    # secondary modes of the single-scale path (device-resident only)
+    "single_1080p_exact": dict(batch=64, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="exact"),
+    "fixed_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="fixed"),
     # BASELINE config 5: few very large frames; with N > 1 GPUs every pair is split into row
     # bands over all ranks (strong scaling, NCCL all-reduce per iteration + all-gather per level)
     "pyramidal_8k": dict(batch=2, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True),
@@ -263,6 +266,7 @@ def workload_config(name: str, wl: dict) -> dict:
         "height": wl["H"],
         "width": wl["W"],
         "window": WINDOW,
+        "mode": {"exact": "exact (reference operation order)", "fixed": "fixed-point S8.7 (RTL datapath)"}.get(wl.get("variant"), "fast"),
         "l2": "per-step inputs + outputs are far larger than the 126 MB L2, so no flush between iterations",
         "parallelism": ("each pair split into row bands over all ranks: all-reduce of the residual sums per "
                         "iteration, all-gather of the owned rows per level (NCCL)") if wl.get("rowband")
@@ -354,7 +358,19 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     v = torch.empty_like(prev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    if rowband:
+    variant = wl.get("variant")
+    if variant == "fixed":
+        p8, c8 = prev.to(torch.uint8), curr.to(torch.uint8)
+        u16 = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+        v16 = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+
+        def step():
+            of_b200.lk_single_scale_fx_dev(p8.data_ptr(), c8.data_ptr(), u16.data_ptr(), v16.data_ptr(), B, H, W, True, stream)
+    elif variant == "exact":
+        def step():
+            of_b200.lk_single_scale_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
+                                        WINDOW, of_b200.MODE_EXACT, stream)
+    elif rowband:
         import distributed as ofd
 
         backend = ofd.CudaBackend()
@@ -416,6 +432,14 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         from oracle import lk_float_oracle as orc
 
         idx = [0, B // 2, B - 1] if not wl["pyramidal"] else [0]
+        if variant == "fixed":
+            from oracle import lk_fixed_oracle as fxo
+
+            okf = True
+            for b in idx[:2]:
+                uo, vo = fxo.lk_single_scale_fx(prev[b].cpu().numpy().astype(np.uint8), curr[b].cpu().numpy().astype(np.uint8))
+                okf &= bool(np.array_equal(u16[b].cpu().numpy(), uo) and np.array_equal(v16[b].cpu().numpy(), vo))
+            idx = []
         ok = True
         worst, frac_big, mean_diff = 0.0, 0.0, 0.0
         for b in idx:
@@ -435,6 +459,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             worst = max(worst, float(d.max()))
             frac_big = max(frac_big, float((d > 1e-3).mean()))
             mean_diff = max(mean_diff, float(d.mean()))
+        if variant == "fixed":
+            ok, idx = okf, [0, 1]
         parity = {"bit_exact_vs_oracle": ok, "pairs_checked": len(idx), "max_abs_diff_px": worst,
                   "frac_pixels_diff_gt_1e-3": frac_big, "mean_abs_diff_px": mean_diff}
         if wl["pyramidal"] and H * W > 3840 * 2160:
@@ -445,7 +471,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
 
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
     e2e = None
-    if not wl["pyramidal"] and not args.no_e2e:
+    if not wl["pyramidal"] and not args.no_e2e and variant is None:
         e2e = measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier)
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------
@@ -473,7 +499,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         return
 
     peak, peak_src = hbm_peak()
-    bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else 16.0
+    bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else (6.0 if variant == "fixed" else 16.0)
     kernel_ms = statistics.mean(per_step)
     achieved = bpp * pixels_per_step / (kernel_ms * 1e-3) / 1e9
     line = {
@@ -487,7 +513,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         "higher_is_better": True,
         "scaling": "strong" if rowband else "weak",
         "vs_baseline": None,
-        "dtype": "f32",
+        "dtype": "i32" if variant == "fixed" else "f32",
         "data": "synthetic",
         "config": workload_config(args.workload, wl),
         "frame_pairs_per_s": jobs * B / (ms_per_step * 1e-3),
@@ -503,7 +529,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             "algorithmic_bytes": bpp * pixels_per_step,
             "peak_source": peak_src,
             "algorithmic_bytes_per_pixel": bpp,
-            "kernel": "lk_march_kernel<true> (one launch per step)" if not wl["pyramidal"] else "whole pyramidal step (all launches)",
+            "kernel": ("whole pyramidal step (all launches)" if wl["pyramidal"] else
+                       {"fixed": "lk_fixed_kernel", "exact": "lk_tile_kernel<SRC_FRAMES, 5>"}.get(variant, "lk_march_kernel<true, false> (one launch per step)")),
             "kernel_ms": kernel_ms,
             "frac_of_nominal_8TBs": achieved / 8000.0,
         },
