@@ -113,6 +113,10 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
                                 const double* weights, int radius, int row_lo, int row_hi, int* launches,
                                 cudaStream_t stream);
+// the same level by the marching kernel (pyramid_march.cu): radius 8, decimation step in [1, 6]
+bool pyramid_march_supported(int H, int W, int oh, int ow, int radius);
+cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
+                                 const double* weights, int row_lo, int row_hi, int* launches, cudaStream_t stream);
 cudaError_t launch_warp(const float* img, const float* fu, const float* fv, float* out, int batch, int H, int W,
                         int* launches, cudaStream_t stream);
 // coarse flow (selected ping-pong buffer) -> fine grid, scaled (lucas_kanade_pyramidal.py:100-138)

@@ -11,6 +11,8 @@
 //   each axis, rows (axis 0) first, 'reflect' boundary.  map_coordinates(order=1,
 //   mode="constant"): float64 coordinates and blend, outside -> exactly 0.
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "of_common.cuh"
 #include "of_kernels.h"
@@ -220,6 +222,15 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
                                 cudaStream_t stream) {
     if (radius < 0 || radius > PYR_MAX_RADIUS || oh < 1 || ow < 1 || batch > 65535) return cudaErrorInvalidValue;
     if (row_lo < 0 || row_hi > oh || row_lo >= row_hi) return cudaErrorInvalidValue;
+    // sigma = 2 (the reference's pyramid) on a ~2x decimation: the marching kernel; anything else
+    // (and OF_B200_PYRAMID=tile, for A/B measurements) takes the generic tile kernel below.  Both
+    // produce the same bits.
+    static const bool force_tile = [] {
+        const char* e = getenv("OF_B200_PYRAMID");
+        return e != nullptr && strcmp(e, "tile") == 0;
+    }();
+    if (!force_tile && pyramid_march_supported(H, W, oh, ow, radius))
+        return launch_pyramid_march(src, dst, batch, H, W, oh, ow, weights, row_lo, row_hi, launches, stream);
     PyrArgs a;
     a.src = src;
     a.dst = dst;
@@ -293,48 +304,81 @@ struct UpArgs {
     float scale_y, scale_x;
 };
 
-// One thread = one target column and UP_ROWS target rows: the column's coordinate, taps and
-// weights are computed once, and u and v share every row's coordinate and weights.  The
+// One thread = one target column and UP_ROWS consecutive target rows: the column's coordinate,
+// taps and weights are computed once, u and v share every row's coordinate and weights, and the
+// converted coarse taps are kept while consecutive target rows fall between the same two coarse
+// rows (every other row at 2x), so each coarse value is loaded and widened once per thread.  The
 // linspace grid never leaves [0, n - 1], so every sample is inside the coarse field.
-constexpr int UP_ROWS = 8;
+constexpr int UP_ROWS = 16;
 
 __global__ void __launch_bounds__(256) upsample_flow_kernel(UpArgs a) {
+    // the rows' coordinates are the same for every column: 16 threads compute them once per CTA
+    __shared__ int s_y0[UP_ROWS], s_y1[UP_ROWS];
+    __shared__ double s_fy[UP_ROWS], s_wy0[UP_ROWS];
+    const int y_begin = a.row_lo + blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.row_hi);
+    if (threadIdx.x < UP_ROWS) {
+        const int y = min(y_begin + (int)threadIdx.x, a.th - 1);
+        const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
+        const double fy0 = floor(yc);
+        const double fy = dsub(yc, fy0);
+        const int y0 = (int)fy0;
+        s_y0[threadIdx.x] = y0;
+        s_y1[threadIdx.x] = min(y0 + 1, a.ch - 1);
+        s_fy[threadIdx.x] = fy;
+        s_wy0[threadIdx.x] = dsub(1.0, fy);
+    }
+    __syncthreads();
     const int x = blockIdx.x * 256 + threadIdx.x;
     if (x >= a.tw) return;
     const int pair = blockIdx.z;
     const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
     const size_t cplane = (size_t)a.ch * a.cw;
-    const float* __restrict__ cu = a.cu[cur] + pair * cplane;
-    const float* __restrict__ cv = a.cv[cur] + pair * cplane;
-    float* __restrict__ fu = a.fu + (size_t)pair * a.th * a.tw;
-    float* __restrict__ fv = a.fv + (size_t)pair * a.th * a.tw;
+    const float* __restrict__ cu = (cur ? a.cu[1] : a.cu[0]) + pair * cplane;
+    const float* __restrict__ cv = (cur ? a.cv[1] : a.cv[0]) + pair * cplane;
+    const size_t o0 = (size_t)pair * a.th * a.tw + (size_t)y_begin * a.tw + x;
+    float* __restrict__ fu = a.fu + o0;
+    float* __restrict__ fv = a.fv + o0;
 
     const double xc = linspace_coord(x, a.tw, a.cw, a.step_x);
     const double fx0 = floor(xc);
     const double fx = dsub(xc, fx0), wx0 = dsub(1.0, fx);
     const int x0 = (int)fx0;
     const int x1 = min(x0 + 1, a.cw - 1);  // weight 0 when it would leave the field
-    const int y_begin = a.row_lo + blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.row_hi);
-    for (int y = y_begin; y < y_end; ++y) {
-        const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
-        const double fy0 = floor(yc);
-        const double fy = dsub(yc, fy0), wy0 = dsub(1.0, fy);
-        const int y0 = (int)fy0;
-        const int y1 = min(y0 + 1, a.ch - 1);
-        const size_t r0 = (size_t)y0 * a.cw, r1 = (size_t)y1 * a.cw;
+    int cy0 = -1, cy1 = -1;  // coarse rows held in (u0*, v0*) and (u1*, v1*)
+    double u00 = 0.0, u01 = 0.0, u10 = 0.0, u11 = 0.0, v00 = 0.0, v01 = 0.0, v10 = 0.0, v11 = 0.0;
+    const int n = y_end - y_begin;
+    for (int k = 0; k < n; ++k) {
+        const int y0 = s_y0[k], y1 = s_y1[k];
+        const double fy = s_fy[k], wy0 = s_wy0[k];
+        if (y0 != cy0) {  // uniform over the CTA
+            if (y0 == cy1) {
+                u00 = u10; u01 = u11; v00 = v10; v01 = v11;
+            } else {
+                const unsigned r0 = (unsigned)(y0 * a.cw);
+                u00 = (double)__ldg(cu + r0 + x0); u01 = (double)__ldg(cu + r0 + x1);
+                v00 = (double)__ldg(cv + r0 + x0); v01 = (double)__ldg(cv + r0 + x1);
+            }
+            cy0 = y0;
+        }
+        if (y1 != cy1) {
+            const unsigned r1 = (unsigned)(y1 * a.cw);
+            u10 = (double)__ldg(cu + r1 + x0); u11 = (double)__ldg(cu + r1 + x1);
+            v10 = (double)__ldg(cv + r1 + x0); v11 = (double)__ldg(cv + r1 + x1);
+            cy1 = y1;
+        }
         // map_coordinates order: taps row-major, each (value * wy) * wx, summed from 0.0
         double tu = 0.0, tv = 0.0;
-        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r0 + x0), wy0), wx0));
-        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r0 + x1), wy0), fx));
-        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r1 + x0), fy), wx0));
-        tu = dadd(tu, dmul(dmul((double)__ldg(cu + r1 + x1), fy), fx));
-        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r0 + x0), wy0), wx0));
-        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r0 + x1), wy0), fx));
-        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r1 + x0), fy), wx0));
-        tv = dadd(tv, dmul(dmul((double)__ldg(cv + r1 + x1), fy), fx));
-        const size_t o = (size_t)y * a.tw + x;
-        fu[o] = fmul((float)tu, a.scale_x);  // flow scales with the resolution, float32 multiply
-        fv[o] = fmul((float)tv, a.scale_y);
+        tu = dadd(tu, dmul(dmul(u00, wy0), wx0));
+        tu = dadd(tu, dmul(dmul(u01, wy0), fx));
+        tu = dadd(tu, dmul(dmul(u10, fy), wx0));
+        tu = dadd(tu, dmul(dmul(u11, fy), fx));
+        tv = dadd(tv, dmul(dmul(v00, wy0), wx0));
+        tv = dadd(tv, dmul(dmul(v01, wy0), fx));
+        tv = dadd(tv, dmul(dmul(v10, fy), wx0));
+        tv = dadd(tv, dmul(dmul(v11, fy), fx));
+        const unsigned o = (unsigned)(k * a.tw);
+        __stcs(fu + o, fmul((float)tu, a.scale_x));  // flow scales with the resolution, float32 multiply
+        __stcs(fv + o, fmul((float)tv, a.scale_y));
     }
 }
 

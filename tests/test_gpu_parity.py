@@ -415,6 +415,45 @@ def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
     assert np.isnan(un[:10]).all() and np.isnan(un[37:]).all()  # rows outside the range untouched
 
 
+@pytest.mark.parametrize("shape", [(16, 248), (135, 249), (300, 517), (333, 1000), (1080, 1920)])
+def test_pyramid_marching_kernel_against_oracle(ofb, shape):
+    """One pyramid level by the marching kernel (frames >= 16 x 248) on general floats, odd sizes,
+    a batch, and a row range; bit-exact against the SciPy-order oracle."""
+    import torch
+
+    H, W = shape
+    rng = np.random.default_rng(H * 7 + W)
+    imgs = (rng.standard_normal((3, H, W)) * 60.0 + 100.0).astype(np.float32)
+    oh, ow = H // 2, W // 2
+    want = np.stack([orc.build_gaussian_pyramid(im, 2)[0] for im in imgs])
+    assert want.shape == (3, oh, ow)
+    assert_bit_equal(ofb.pyramid_down(imgs[1]), want[1], "host entry point")
+    dev = torch.device("cuda", 0)
+    src = torch.from_numpy(imgs).to(dev)
+    dst = torch.full((3, oh, ow), float("nan"), dtype=torch.float32, device=dev)
+    ofb.pyramid_down_dev(src.data_ptr(), dst.data_ptr(), 3, H, W, oh, ow)
+    torch.cuda.synchronize()
+    assert_bit_equal(dst.cpu().numpy(), want, "batch of 3")
+    lo, hi = oh // 3, oh - 1
+    dst.fill_(float("nan"))
+    ofb.pyramid_down_dev(src.data_ptr(), dst.data_ptr(), 3, H, W, oh, ow, row_lo=lo, row_hi=hi)
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    assert_bit_equal(got[:, lo:hi], want[:, lo:hi], "row range")
+    assert np.isnan(got[:, :lo]).all() and np.isnan(got[:, hi:]).all()
+
+
+def test_upsample_flow_large_against_oracle(ofb):
+    rng = np.random.default_rng(5)
+    cu = (rng.standard_normal((135, 240)) * 3).astype(np.float32)
+    cv = (rng.standard_normal((135, 240)) * 3).astype(np.float32)
+    for shape in ((270, 480), (271, 481), (400, 700)):
+        wu, wv = orc.upsample_flow(cu, cv, shape)
+        gu, gv = ofb.upsample_flow(cu, cv, shape)
+        assert_bit_equal(gu, wu, f"upsample u {shape}")
+        assert_bit_equal(gv, wv, f"upsample v {shape}")
+
+
 # ---------------------------------------------------------------------------------------
 # edge cases of the boundary
 # ---------------------------------------------------------------------------------------
