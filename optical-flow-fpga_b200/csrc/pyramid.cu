@@ -382,6 +382,73 @@ __global__ void __launch_bounds__(256) upsample_flow_kernel(UpArgs a) {
     }
 }
 
+// Upsampling proper (target about twice the coarse size -- every call of the pyramidal path): the
+// coarse tile a CTA needs (<= 10 rows x 132 columns of u and v) is loaded once, coalesced, widened
+// to float64 on the way into shared memory, and every target pixel takes its 8 taps from there:
+// no global-load latency and no conversions inside the row loop.
+constexpr int UPS_CR = 10, UPS_CC = 132;
+
+__global__ void __launch_bounds__(256) upsample_flow_tile_kernel(UpArgs a) {
+    __shared__ int s_y0[UP_ROWS], s_y1[UP_ROWS];
+    __shared__ double s_fy[UP_ROWS], s_wy0[UP_ROWS];
+    __shared__ double s_u[UPS_CR * UPS_CC], s_v[UPS_CR * UPS_CC];
+    const int y_begin = a.row_lo + blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.row_hi);
+    const int xb = blockIdx.x * 256;
+    const int pair = blockIdx.z;
+    const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
+    const size_t cplane = (size_t)a.ch * a.cw;
+    const float* __restrict__ cu = (cur ? a.cu[1] : a.cu[0]) + pair * cplane;
+    const float* __restrict__ cv = (cur ? a.cv[1] : a.cv[0]) + pair * cplane;
+    const int yf = (int)floor(linspace_coord(y_begin, a.th, a.ch, a.step_y));  // first coarse row / column
+    const int xf = (int)floor(linspace_coord(xb, a.tw, a.cw, a.step_x));
+    if (threadIdx.x < UP_ROWS) {
+        const int y = min(y_begin + (int)threadIdx.x, a.th - 1);
+        const double yc = linspace_coord(y, a.th, a.ch, a.step_y);
+        const double fy0 = floor(yc);
+        const double fy = dsub(yc, fy0);
+        const int y0 = (int)fy0;
+        s_y0[threadIdx.x] = (y0 - yf) * UPS_CC;
+        s_y1[threadIdx.x] = (min(y0 + 1, a.ch - 1) - yf) * UPS_CC;
+        s_fy[threadIdx.x] = fy;
+        s_wy0[threadIdx.x] = dsub(1.0, fy);
+    }
+    for (int i = threadIdx.x; i < UPS_CR * UPS_CC; i += 256) {
+        const int r = i / UPS_CC, c = i - r * UPS_CC;
+        const unsigned o = (unsigned)(min(yf + r, a.ch - 1) * a.cw + min(xf + c, a.cw - 1));
+        s_u[i] = (double)__ldg(cu + o);
+        s_v[i] = (double)__ldg(cv + o);
+    }
+    __syncthreads();
+    const int x = xb + threadIdx.x;
+    if (x >= a.tw) return;
+    const size_t o0 = (size_t)pair * a.th * a.tw + (size_t)y_begin * a.tw + x;
+    float* __restrict__ fu = a.fu + o0;
+    float* __restrict__ fv = a.fv + o0;
+    const double xc = linspace_coord(x, a.tw, a.cw, a.step_x);
+    const double fx0 = floor(xc);
+    const double fx = dsub(xc, fx0), wx0 = dsub(1.0, fx);
+    const int x0 = (int)fx0 - xf;
+    const int x1 = min((int)fx0 + 1, a.cw - 1) - xf;  // weight 0 when it would leave the field
+    const int n = y_end - y_begin;
+    for (int k = 0; k < n; ++k) {
+        const int r0 = s_y0[k], r1 = s_y1[k];
+        const double fy = s_fy[k], wy0 = s_wy0[k];
+        // map_coordinates order: taps row-major, each (value * wy) * wx, summed from 0.0
+        double tu = 0.0, tv = 0.0;
+        tu = dadd(tu, dmul(dmul(s_u[r0 + x0], wy0), wx0));
+        tu = dadd(tu, dmul(dmul(s_u[r0 + x1], wy0), fx));
+        tu = dadd(tu, dmul(dmul(s_u[r1 + x0], fy), wx0));
+        tu = dadd(tu, dmul(dmul(s_u[r1 + x1], fy), fx));
+        tv = dadd(tv, dmul(dmul(s_v[r0 + x0], wy0), wx0));
+        tv = dadd(tv, dmul(dmul(s_v[r0 + x1], wy0), fx));
+        tv = dadd(tv, dmul(dmul(s_v[r1 + x0], fy), wx0));
+        tv = dadd(tv, dmul(dmul(s_v[r1 + x1], fy), fx));
+        const unsigned o = (unsigned)(k * a.tw);
+        __stcs(fu + o, fmul((float)tu, a.scale_x));  // flow scales with the resolution, float32 multiply
+        __stcs(fv + o, fmul((float)tv, a.scale_y));
+    }
+}
+
 cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float* cu1, const float* cv1,
                                  const int* sel, int sel_xor, float* fu, float* fv, int batch, int ch, int cw, int th,
                                  int tw, int row_lo, int row_hi, int* launches, cudaStream_t stream) {
@@ -407,7 +474,11 @@ cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float
     a.scale_x = (float)((double)tw / (double)cw);
     if (launches) *launches += 1;
     dim3 grid((tw + 255) / 256, (row_hi - row_lo + UP_ROWS - 1) / UP_ROWS, batch);
-    upsample_flow_kernel<<<grid, 256, 0, stream>>>(a);
+    // the staged tile covers 16 target rows x 256 target columns when the grid steps are <= ~0.5
+    if (15.0 * a.step_y + 1.0 < UPS_CR - 1 && 255.0 * a.step_x + 1.0 < UPS_CC - 1)
+        upsample_flow_tile_kernel<<<grid, 256, 0, stream>>>(a);
+    else
+        upsample_flow_kernel<<<grid, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

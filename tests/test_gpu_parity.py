@@ -447,7 +447,9 @@ def test_upsample_flow_large_against_oracle(ofb):
     rng = np.random.default_rng(5)
     cu = (rng.standard_normal((135, 240)) * 3).astype(np.float32)
     cv = (rng.standard_normal((135, 240)) * 3).astype(np.float32)
-    for shape in ((270, 480), (271, 481), (400, 700)):
+    # (270, 480) ... take the staged-tile kernel (grid step <= ~0.5); (180, 300) and (100, 200) have
+    # steps of 0.75 / 1.35 and take the generic one
+    for shape in ((270, 480), (271, 481), (400, 700), (180, 300), (100, 200)):
         wu, wv = orc.upsample_flow(cu, cv, shape)
         gu, gv = ofb.upsample_flow(cu, cv, shape)
         assert_bit_equal(gu, wu, f"upsample u {shape}")
