@@ -168,6 +168,39 @@ int of_lk_convergence_update_dev(const double* sums, int batch, double n_pixels,
 int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
                               int batch, int height, int width, int flags, void* stream);
 
+/* ---- row-band multi-GPU mode of lucas_kanade_pyramidal, native driver ---------------------
+ * One frame pair, the rows of every pyramid level split over `world` ranks (one process -- or
+ * thread -- per GPU of one NVLink / NVSwitch domain).  The reference has no multi-device path;
+ * this is lucas_kanade_pyramidal (python/lucas_kanade_pyramidal.py:141-228) for frames too large
+ * or too urgent for one GPU, with results bit-identical to of_lk_pyramidal_f32_dev.
+ *
+ * Every rank creates a context (which allocates its "arena" with one cudaMalloc), publishes the
+ * arena to the other ranks -- of_rowband_ipc_handle / of_rowband_open_peers_ipc between
+ * processes (the 64-byte handles travel over any channel, e.g. torch.distributed
+ * all_gather_object), of_rowband_set_peers between threads of one process -- and then calls
+ * of_rowband_run on a stream of its device: the call only enqueues kernels; pyramid rows, final
+ * flow rows and the per-iteration residual sums move between the GPUs by peer stores and flag
+ * words inside those kernels (no NCCL, no host round trip).  All ranks must issue the same
+ * sequence of of_rowband_run calls. */
+#define OF_IPC_HANDLE_BYTES 64
+typedef struct of_rowband of_rowband_t;
+
+int of_rowband_create(of_rowband_t** ctx, int rank, int world, int height, int width, int levels, int window,
+                      int iterations, int mode, const double* gauss_weights, int gauss_radius);
+size_t of_rowband_arena_bytes(const of_rowband_t* ctx);
+void* of_rowband_arena(const of_rowband_t* ctx); /* device pointer of this rank's arena */
+int of_rowband_ipc_handle(const of_rowband_t* ctx, void* handle_out /* OF_IPC_HANDLE_BYTES */);
+int of_rowband_open_peers_ipc(of_rowband_t* ctx, const void* handles /* world x OF_IPC_HANDLE_BYTES, rank order */);
+int of_rowband_set_peers(of_rowband_t* ctx, void* const* arenas /* world device pointers, rank order */);
+/* prev, curr: the full [height][width] frames on this rank's device.  u, v: optional full-size
+ * outputs (device); with NULL the result stays in the arena (of_rowband_result). */
+int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, float* u, float* v, void* stream);
+int of_rowband_result(const of_rowband_t* ctx, const float** u, const float** v);
+/* waits for `stream`, then copies out (each optional) iters_executed[levels] (level 0 = coarsest),
+ * residuals[levels][iterations][2] and the error word (non-zero: a peer did not answer in time) */
+int of_rowband_trace(of_rowband_t* ctx, int* iters_executed, float* residuals, int* error, void* stream);
+int of_rowband_destroy(of_rowband_t* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,8 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / os.environ.get("OF_B200_LIB_NAME", "libof_b200.so")  # variants: experiments only
-SOURCES = ["of_api.cu", "lk_march.cu", "lk_tile.cu", "pyramid.cu", "pyramid_march.cu", "lk_fixed.cu"]
-HEADERS = ["of_common.cuh", "of_kernels.h", "../../include/of_b200.h"]
+SOURCES = ["of_api.cu", "lk_march.cu", "lk_tile.cu", "pyramid.cu", "pyramid_march.cu", "peer.cu", "lk_fixed.cu"]
+HEADERS = ["of_common.cuh", "of_kernels.h", "of_rowband.inl", "../../include/of_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

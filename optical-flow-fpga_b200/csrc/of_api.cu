@@ -817,3 +817,5 @@ int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, 
 }
 
 }  // extern "C"
+
+#include "of_rowband.inl"

@@ -128,6 +128,28 @@ cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1
                                int sel_xor, float* out_u, float* out_v, int batch, size_t n, int* launches,
                                cudaStream_t stream);
 
+// ---- peer-memory collectives of the row-band mode (peer.cu) ----------------------------
+constexpr int PEER_MAX_WORLD = 8;  // one NVSwitch domain
+constexpr int PEER_SLOTS = 64;     // flag / exchange slots, indexed by sequence number
+struct PeerView {
+    char* peer[PEER_MAX_WORLD];  // arena base of every rank as mapped in this process (peer[rank] = own)
+    int world, rank;
+    size_t flag_off, xchg_off;   // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD]; double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
+    int* err;                    // sticky error word in the local arena (a wait timed out)
+    unsigned long long timeout_ns;
+};
+// rows of a plane (current ping-pong buffer: sel[0] ^ sel_xor ? src1 : src0) -> byte offset dst_off
+// of every rank's arena; `first` / `count` in elements
+cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
+                                  size_t dst_off, size_t first, size_t count, bool skip_self, int* launches,
+                                  cudaStream_t stream);
+// signal sequence number `seq` to every rank and wait for every rank's
+cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long seq, int* launches, cudaStream_t stream);
+// all-reduce of (sum|du|, sum|dv|) + the reference's convergence test + ping-pong flip, in one kernel
+cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long seq, const double* partial, int blocks,
+                                         double n_pixels, int* sel, int* done, int* iters_executed, float* residuals,
+                                         int iteration, int* launches, cudaStream_t stream);
+
 // ---- fixed-point mode (lk_fixed.cu) ----------------------------------------------------
 cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,
                             int mirror_avg_quirk, int* launches, cudaStream_t stream);

@@ -1,0 +1,263 @@
+// Collectives of the row-band (multi-GPU) pyramidal path over NVLink / NVSwitch peer memory.
+//
+// Every rank owns one "arena" (a single cudaMalloc) with the same layout; peers map each other's
+// arenas (CUDA IPC between processes, plain pointers between threads of one process), so a rank
+// addresses any peer's copy of a plane as peer_base + offset.  Three device-side primitives, all
+// stream-ordered, none of them touching the host or NCCL:
+//
+//   push_rows        all-gather by stores: the rows a rank owns go straight into every peer's
+//                    arena (and its own "gathered" plane), read once, written `world` times;
+//   peer_sync        release-store of a sequence number into every peer's flag slot, then an
+//                    acquire-spin until every rank's number has arrived (the rows pushed before are
+//                    then visible): the barrier that ends an all-gather;
+//   allreduce_update the reference's global early-exit test (lucas_kanade_pyramidal.py:213-223)
+//                    for row bands: reduce this rank's per-block |du|, |dv| partials, publish the
+//                    two sums in every peer's exchange slot, wait for all ranks, add them in rank
+//                    order (so every rank takes the same decision), flip the ping-pong selector.
+//
+// Sequence numbers only grow and a slot is reused after PEER_SLOTS collectives, while no rank can
+// run more than one collective ahead of the slowest one, so flags never need a reset.  Every spin
+// has a time-out (a peer that died must not hang the GPU): it sets a sticky error word that makes
+// all later waits fall through; the host reads it after the run.
+#include <cuda_runtime.h>
+
+#include "of_common.cuh"
+#include "of_kernels.h"
+
+namespace ofb {
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// wait until flags[slot][r] >= seq; false on time-out or when an earlier wait already failed
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, int* err,
+                                          unsigned long long timeout_ns) {
+    if (*reinterpret_cast<volatile int*>(err) != 0) return false;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(flag) < seq) {
+        if ((++spins & 63u) == 0) {
+            if (global_timer_ns() - t0 > timeout_ns) {
+                atomicExch(err, 1);
+                return false;
+            }
+            __nanosleep(200);
+        }
+    }
+    return true;
+}
+
+struct PushArgs {
+    const float* src[2];  // ping-pong candidates (same plane offsets), current = sel ? src[1] : src[0]
+    const int* sel;       // nullable
+    int sel_xor;
+    size_t dst_off;       // byte offset of the gathered plane in every arena
+    char* peer[PEER_MAX_WORLD];
+    int world;
+    int skip;             // rank not to write to (-1: none): the source already is that rank's plane
+    size_t first;         // first element (row_a * W) and number of elements (rows * W) to push
+    size_t count;
+};
+
+__global__ void __launch_bounds__(256) push_rows_kernel(const PushArgs a) {
+    const int cur = (a.sel ? a.sel[0] : 0) ^ a.sel_xor;
+    const float* __restrict__ src = (cur ? a.src[1] : a.src[0]) + a.first;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | (a.dst_off + a.first * 4)) & 15) == 0;
+    const size_t n4 = vec ? a.count / 4 : 0;
+    for (size_t i = tid; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+#pragma unroll
+        for (int r = 0; r < PEER_MAX_WORLD; ++r)
+            if (r < a.world && r != a.skip) reinterpret_cast<float4*>(a.peer[r] + a.dst_off + a.first * 4)[i] = v;
+    }
+    for (size_t i = n4 * 4 + tid; i < a.count; i += stride) {
+        const float v = __ldg(src + i);
+#pragma unroll
+        for (int r = 0; r < PEER_MAX_WORLD; ++r)
+            if (r < a.world && r != a.skip) reinterpret_cast<float*>(a.peer[r] + a.dst_off + a.first * 4)[i] = v;
+    }
+}
+
+struct SyncArgs {
+    char* peer[PEER_MAX_WORLD];
+    int world, rank;
+    size_t flag_off;  // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD] in every arena
+    size_t xchg_off;  // double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
+    unsigned long long seq;
+    int* err;
+    unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(32) peer_sync_kernel(const SyncArgs a) {
+    const int r = threadIdx.x;
+    const int slot = (int)(a.seq % PEER_SLOTS);
+    if (r < a.world) {
+        __threadfence_system();  // the rows pushed by the kernels before this one
+        st_release_sys(reinterpret_cast<unsigned long long*>(a.peer[r] + a.flag_off) + slot * PEER_MAX_WORLD + a.rank, a.seq);
+        wait_flag(reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.flag_off) + slot * PEER_MAX_WORLD + r, a.seq,
+                  a.err, a.timeout_ns);
+    }
+}
+
+struct AllreduceArgs {
+    SyncArgs s;
+    const double* partial;  // this rank's per-block sums of |du|, |dv| (nullptr: the rank owns no rows)
+    int blocks;
+    double n_pixels;
+    int* sel;
+    int* done;
+    int* iters_executed;
+    float* residuals;  // [max_iters][2]
+    int iteration;
+};
+
+__global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const AllreduceArgs a) {
+    __shared__ double red[2][8];
+    __shared__ double tot[PEER_MAX_WORLD][2];
+    __shared__ int ok[PEER_MAX_WORLD];
+    if (a.done[0]) {
+        // the level has converged: the ranks agree on that, nothing is exchanged for this iteration
+        return;
+    }
+    double su = 0.0, sv = 0.0;
+    if (a.partial != nullptr) {
+        for (int i = threadIdx.x; i < a.blocks; i += 256) {
+            su += a.partial[2 * i];
+            sv += a.partial[2 * i + 1];
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        su += __shfl_down_sync(0xffffffffu, su, off);
+        sv += __shfl_down_sync(0xffffffffu, sv, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = su;
+        red[1][threadIdx.x >> 5] = sv;
+    }
+    __syncthreads();
+    const int r = threadIdx.x, slot = (int)(a.s.seq % PEER_SLOTS);
+    if (r < a.s.world) {
+        su = 0.0;
+        sv = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            su += red[0][w];
+            sv += red[1][w];
+        }
+        // publish (su, sv) in peer r's slot of this rank, then the flag
+        double* x = reinterpret_cast<double*>(a.s.peer[r] + a.s.xchg_off) + ((size_t)slot * PEER_MAX_WORLD + a.s.rank) * 2;
+        x[0] = su;
+        x[1] = sv;
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(a.s.peer[r] + a.s.flag_off) + slot * PEER_MAX_WORLD + a.s.rank,
+                       a.s.seq);
+        // collect rank r's contribution from the local arena
+        const bool got = wait_flag(reinterpret_cast<const unsigned long long*>(a.s.peer[a.s.rank] + a.s.flag_off) +
+                                       slot * PEER_MAX_WORLD + r,
+                                   a.s.seq, a.s.err, a.s.timeout_ns);
+        const double* y = reinterpret_cast<const double*>(a.s.peer[a.s.rank] + a.s.xchg_off) + ((size_t)slot * PEER_MAX_WORLD + r) * 2;
+        tot[r][0] = got ? *reinterpret_cast<const volatile double*>(y) : 0.0;
+        tot[r][1] = got ? *reinterpret_cast<const volatile double*>(y + 1) : 0.0;
+        ok[r] = got ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tu = 0.0, tv = 0.0;
+        bool all = true;
+        for (int q = 0; q < a.s.world; ++q) {  // rank order: the same sum on every rank
+            tu += tot[q][0];
+            tv += tot[q][1];
+            all = all && ok[q];
+        }
+        if (!all) {
+            a.done[0] = 1;  // a peer never answered: stop iterating (the error word is set)
+            return;
+        }
+        const float mu = (float)(tu / a.n_pixels), mv = (float)(tv / a.n_pixels);
+        a.sel[0] ^= 1;
+        if (a.iters_executed) a.iters_executed[0] += 1;
+        if (a.residuals) {
+            a.residuals[2 * a.iteration + 0] = mu;
+            a.residuals[2 * a.iteration + 1] = mv;
+        }
+        if (mu < OF_CONVERGENCE_EPS && mv < OF_CONVERGENCE_EPS) a.done[0] = 1;
+    }
+}
+
+}  // namespace
+
+static void fill_sync(SyncArgs& s, const PeerView& pv, unsigned long long seq) {
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) s.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
+    s.world = pv.world;
+    s.rank = pv.rank;
+    s.flag_off = pv.flag_off;
+    s.xchg_off = pv.xchg_off;
+    s.seq = seq;
+    s.err = pv.err;
+    s.timeout_ns = pv.timeout_ns;
+}
+
+cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
+                                  size_t dst_off, size_t first, size_t count, bool skip_self, int* launches,
+                                  cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    PushArgs a;
+    a.src[0] = src0;
+    a.src[1] = src1 ? src1 : src0;
+    a.sel = sel;
+    a.sel_xor = sel_xor;
+    a.dst_off = dst_off;
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) a.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
+    a.world = pv.world;
+    a.skip = skip_self ? pv.rank : -1;
+    a.first = first;
+    a.count = count;
+    size_t blocks = (count / 4 + 256 * 4 - 1) / (256 * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (launches) *launches += 1;
+    push_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long seq, int* launches, cudaStream_t stream) {
+    SyncArgs s;
+    fill_sync(s, pv, seq);
+    if (launches) *launches += 1;
+    peer_sync_kernel<<<1, 32, 0, stream>>>(s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long seq, const double* partial, int blocks,
+                                         double n_pixels, int* sel, int* done, int* iters_executed, float* residuals,
+                                         int iteration, int* launches, cudaStream_t stream) {
+    AllreduceArgs a;
+    fill_sync(a.s, pv, seq);
+    a.partial = partial;
+    a.blocks = blocks;
+    a.n_pixels = n_pixels;
+    a.sel = sel;
+    a.done = done;
+    a.iters_executed = iters_executed;
+    a.residuals = residuals;
+    a.iteration = iteration;
+    if (launches) *launches += 1;
+    peer_allreduce_update_kernel<<<1, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace ofb

@@ -391,7 +391,7 @@ constexpr int UPS_CR = 10, UPS_CC = 132;
 __global__ void __launch_bounds__(256) upsample_flow_tile_kernel(UpArgs a) {
     __shared__ int s_y0[UP_ROWS], s_y1[UP_ROWS];
     __shared__ double s_fy[UP_ROWS], s_wy0[UP_ROWS];
-    __shared__ double s_u[UPS_CR * UPS_CC], s_v[UPS_CR * UPS_CC];
+    __shared__ double2 s_uv[UPS_CR * UPS_CC];  // (u, v) of every staged coarse pixel
     const int y_begin = a.row_lo + blockIdx.y * UP_ROWS, y_end = min(y_begin + UP_ROWS, a.row_hi);
     const int xb = blockIdx.x * 256;
     const int pair = blockIdx.z;
@@ -415,8 +415,7 @@ __global__ void __launch_bounds__(256) upsample_flow_tile_kernel(UpArgs a) {
     for (int i = threadIdx.x; i < UPS_CR * UPS_CC; i += 256) {
         const int r = i / UPS_CC, c = i - r * UPS_CC;
         const unsigned o = (unsigned)(min(yf + r, a.ch - 1) * a.cw + min(xf + c, a.cw - 1));
-        s_u[i] = (double)__ldg(cu + o);
-        s_v[i] = (double)__ldg(cv + o);
+        s_uv[i] = make_double2((double)__ldg(cu + o), (double)__ldg(cv + o));
     }
     __syncthreads();
     const int x = xb + threadIdx.x;
@@ -430,19 +429,37 @@ __global__ void __launch_bounds__(256) upsample_flow_tile_kernel(UpArgs a) {
     const int x0 = (int)fx0 - xf;
     const int x1 = min((int)fx0 + 1, a.cw - 1) - xf;  // weight 0 when it would leave the field
     const int n = y_end - y_begin;
+    // the taps stay in registers while consecutive target rows fall between the same coarse rows
+    int c0 = -1, c1 = -1;
+    double2 t00 = make_double2(0.0, 0.0), t01 = t00, t10 = t00, t11 = t00;
     for (int k = 0; k < n; ++k) {
         const int r0 = s_y0[k], r1 = s_y1[k];
         const double fy = s_fy[k], wy0 = s_wy0[k];
+        if (r0 != c0) {  // uniform over the CTA
+            if (r0 == c1) {
+                t00 = t10;
+                t01 = t11;
+            } else {
+                t00 = s_uv[r0 + x0];
+                t01 = s_uv[r0 + x1];
+            }
+            c0 = r0;
+        }
+        if (r1 != c1) {
+            t10 = s_uv[r1 + x0];
+            t11 = s_uv[r1 + x1];
+            c1 = r1;
+        }
         // map_coordinates order: taps row-major, each (value * wy) * wx, summed from 0.0
         double tu = 0.0, tv = 0.0;
-        tu = dadd(tu, dmul(dmul(s_u[r0 + x0], wy0), wx0));
-        tu = dadd(tu, dmul(dmul(s_u[r0 + x1], wy0), fx));
-        tu = dadd(tu, dmul(dmul(s_u[r1 + x0], fy), wx0));
-        tu = dadd(tu, dmul(dmul(s_u[r1 + x1], fy), fx));
-        tv = dadd(tv, dmul(dmul(s_v[r0 + x0], wy0), wx0));
-        tv = dadd(tv, dmul(dmul(s_v[r0 + x1], wy0), fx));
-        tv = dadd(tv, dmul(dmul(s_v[r1 + x0], fy), wx0));
-        tv = dadd(tv, dmul(dmul(s_v[r1 + x1], fy), fx));
+        tu = dadd(tu, dmul(dmul(t00.x, wy0), wx0));
+        tu = dadd(tu, dmul(dmul(t01.x, wy0), fx));
+        tu = dadd(tu, dmul(dmul(t10.x, fy), wx0));
+        tu = dadd(tu, dmul(dmul(t11.x, fy), fx));
+        tv = dadd(tv, dmul(dmul(t00.y, wy0), wx0));
+        tv = dadd(tv, dmul(dmul(t01.y, wy0), fx));
+        tv = dadd(tv, dmul(dmul(t10.y, fy), wx0));
+        tv = dadd(tv, dmul(dmul(t11.y, fy), fx));
         const unsigned o = (unsigned)(k * a.tw);
         __stcs(fu + o, fmul((float)tu, a.scale_x));  // flow scales with the resolution, float32 multiply
         __stcs(fv + o, fmul((float)tv, a.scale_y));

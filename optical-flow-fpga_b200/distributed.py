@@ -9,6 +9,11 @@
   border rules apply.  No halo exchange is needed because every rank reads its halo rows
   straight from the (replicated or host-resident) input frame.
 
+* row-band mode (pyramidal) -- two drivers with the same row bookkeeping and the same bits:
+  `lk_pyramidal_rowbands` (Python loop over the `_dev` building blocks, NCCL / gloo collectives,
+  injectable backend: the one the CPU tests drive) and `PeerRowbands` (the native driver:
+  `of_rowband_run`, collectives by peer stores inside the kernels, no NCCL in the data path).
+
 The collectives are plumbing around the C-ABI calls; `compute` defaults to the CUDA backend
 and is injectable so the split / gather logic can be tested on CPU with gloo.
 """
@@ -437,3 +442,87 @@ def lk_pyramidal_rowbands(
         return flow_u, flow_v
     return backend.to_host(flow_u), backend.to_host(flow_v)
 
+
+
+# ======================================================================================
+# Row-band mode, native driver: peer-memory collectives instead of NCCL + Python loop
+# ======================================================================================
+class _CudaArrayView:
+    """Zero-copy view of device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerRowbands:
+    """lucas_kanade_pyramidal for one frame geometry with the rows of every level split over the
+    ranks of the default process group (one process per GPU of one NVLink domain).
+
+    Setup (once): every rank creates its arena and the 64-byte CUDA IPC handles are exchanged with
+    `all_gather_object`.  After that torch.distributed is not used any more: `run` is one C call
+    (`of_rowband_run`) that enqueues the whole coarse-to-fine computation; pyramid rows, final flow
+    rows and the residual sums of every iteration move between the GPUs by peer stores and flag
+    words inside the kernels (csrc/peer.cu).  Without a process group it degenerates to one rank.
+    """
+
+    def __init__(self, height: int, width: int, num_levels: int = 3, window_size: int = 5, num_iterations: int = 3,
+                 mode: Optional[int] = None, device=None):
+        import torch
+
+        import of_b200
+
+        self.torch, self.ofb = torch, of_b200
+        dist = _dist()
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.shape = (int(height), int(width))
+        if mode is None:
+            mode = of_b200.default_mode()
+        self.ctx = of_b200.RowbandContext(self.rank, self.world, height, width, num_levels, window_size, num_iterations, mode)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.ctx.ipc_handle())
+            self.ctx.open_peers_ipc(handles)
+            dist.barrier()  # nobody starts storing into a peer before every rank has mapped every arena
+        pu, pv = self.ctx.result_ptrs()
+        self.u = torch.as_tensor(_CudaArrayView(pu, self.shape), device=self.device)
+        self.v = torch.as_tensor(_CudaArrayView(pv, self.shape), device=self.device)
+
+    def run(self, prev, curr):
+        """prev, curr: full [H, W] float32 CUDA tensors on this rank's device (the same frames on
+        every rank).  Returns (u, v): views of the arena planes that hold the gathered result on
+        every rank once the current stream has finished (overwritten by the next run)."""
+        torch = self.torch
+        for t in (prev, curr):
+            if tuple(t.shape) != self.shape or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("frames must be contiguous float32 CUDA tensors of the planned shape")
+        self.ctx.run(prev.data_ptr(), curr.data_ptr(), None, None, torch.cuda.current_stream(self.device).cuda_stream)
+        return self.u, self.v
+
+    def trace(self):
+        """(iters_executed[levels], residuals[levels, iterations, 2]); raises if a peer timed out."""
+        iters, resid, err = self.ctx.trace(self.torch.cuda.current_stream(self.device).cuda_stream)
+        if err:
+            raise self.ofb.OFBackendError("row-band run: a peer rank did not answer within the time-out")
+        return iters, resid
+
+    def close(self):
+        self.u = self.v = None
+        self.ctx.close()
+
+
+def lk_pyramidal_rowbands_peer(frame_prev, frame_curr, num_levels=3, window_size=5, num_iterations=3, mode=None):
+    """Convenience form of PeerRowbands for one call with NumPy frames: (u, v) as NumPy arrays."""
+    import torch
+
+    plan = PeerRowbands(frame_prev.shape[0], frame_prev.shape[1], num_levels, window_size, num_iterations, mode)
+    try:
+        dev = plan.device
+        p = torch.from_numpy(np.ascontiguousarray(frame_prev, dtype=np.float32)).to(dev)
+        c = torch.from_numpy(np.ascontiguousarray(frame_curr, dtype=np.float32)).to(dev)
+        u, v = plan.run(p, c)
+        plan.trace()  # waits for the stream and checks the error word
+        return u.cpu().numpy(), v.cpu().numpy()
+    finally:
+        plan.close()

@@ -83,6 +83,16 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp],
     ),
+    "of_rowband_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i]),
+    "of_rowband_arena_bytes": (C.c_size_t, [_vp]),
+    "of_rowband_arena": (_vp, [_vp]),
+    "of_rowband_ipc_handle": (_i, [_vp, _vp]),
+    "of_rowband_open_peers_ipc": (_i, [_vp, _vp]),
+    "of_rowband_set_peers": (_i, [_vp, C.POINTER(_vp)]),
+    "of_rowband_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "of_rowband_result": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "of_rowband_trace": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "of_rowband_destroy": (_i, [_vp]),
 }
 
 
@@ -414,3 +424,82 @@ def lk_refine_dev(
 def lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, mirror_avg_quirk=True, stream=0):
     flags = FX_MIRROR_AVG_QUIRK if mirror_avg_quirk else 0
     _check(lib().of_lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, flags, stream))
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class RowbandContext:
+    """Native row-band (multi-GPU) pyramidal LK for ONE frame pair split over `world` ranks.
+
+    Owns this rank's peer-memory arena.  Connect the ranks with `ipc_handle()` /
+    `open_peers_ipc(handles)` (processes; the handles travel over any channel) or
+    `set_peers(arena_pointers)` (threads of one process), then call `run(prev_ptr, curr_ptr)` on
+    every rank: one C call enqueues the whole coarse-to-fine computation, and the ranks exchange
+    pyramid rows, flow rows and residual sums through peer stores inside the kernels.
+    """
+
+    def __init__(self, rank, world, height, width, num_levels=3, window_size=5, num_iterations=3, mode=MODE_FAST,
+                 sigma: float = 2.0):
+        self.rank, self.world, self.height, self.width = int(rank), int(world), int(height), int(width)
+        self.levels, self.iterations = int(num_levels), int(num_iterations)
+        wts = gaussian_weights(sigma)
+        self._ctx = _vp()
+        _check(
+            lib().of_rowband_create(
+                C.byref(self._ctx), self.rank, self.world, self.height, self.width, self.levels, _window(window_size),
+                self.iterations, mode, _ptr(wts), (len(wts) - 1) // 2,
+            )
+        )
+
+    @property
+    def arena_ptr(self) -> int:
+        return int(lib().of_rowband_arena(self._ctx) or 0)
+
+    @property
+    def arena_bytes(self) -> int:
+        return int(lib().of_rowband_arena_bytes(self._ctx))
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().of_rowband_ipc_handle(self._ctx, buf))
+        return buf.raw
+
+    def open_peers_ipc(self, handles) -> None:
+        blob = b"".join(handles)
+        if len(blob) != self.world * IPC_HANDLE_BYTES:
+            raise ValueError("need one 64-byte handle per rank, in rank order")
+        _check(lib().of_rowband_open_peers_ipc(self._ctx, C.c_char_p(blob)))
+
+    def set_peers(self, arena_ptrs) -> None:
+        if len(arena_ptrs) != self.world:
+            raise ValueError("need one arena pointer per rank, in rank order")
+        arr = (_vp * self.world)(*[_vp(int(p)) for p in arena_ptrs])
+        _check(lib().of_rowband_set_peers(self._ctx, arr))
+
+    def run(self, prev_ptr, curr_ptr, u_ptr=None, v_ptr=None, stream=0) -> None:
+        _check(lib().of_rowband_run(self._ctx, prev_ptr, curr_ptr, u_ptr, v_ptr, stream))
+
+    def result_ptrs(self):
+        u, v = _vp(), _vp()
+        _check(lib().of_rowband_result(self._ctx, C.byref(u), C.byref(v)))
+        return int(u.value), int(v.value)
+
+    def trace(self, stream=0):
+        """(iters_executed[levels], residuals[levels, iterations, 2], error) after waiting for `stream`."""
+        iters = np.zeros(self.levels, dtype=np.int32)
+        resid = np.zeros((self.levels, max(self.iterations, 1), 2), dtype=np.float32)
+        err = C.c_int(0)
+        _check(lib().of_rowband_trace(self._ctx, _ptr(iters), _ptr(resid) if self.iterations > 0 else None, C.byref(err), stream))
+        return iters, resid[:, : self.iterations], int(err.value)
+
+    def close(self) -> None:
+        if self._ctx:
+            lib().of_rowband_destroy(self._ctx)
+            self._ctx = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,8 +1,13 @@
 """Shared fixtures.  GPU tests are marked ``@pytest.mark.gpu``; everything else runs on CPU."""
 
 import json
+import os
 import sys
 from pathlib import Path
+
+# The native row-band test runs up to 8 emulated ranks as 8 streams of one device that wait for
+# each other inside kernels: every stream needs its own hardware queue (default: 8 for all streams).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np
 import pytest

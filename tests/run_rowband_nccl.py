@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--mode", choices=["exact", "fast"], default="fast")
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--driver", choices=["nccl", "peer"], default="peer",
+                    help="nccl: Python loop + NCCL collectives; peer: native driver, peer-memory collectives")
     args = ap.parse_args()
     import faulthandler
 
@@ -50,14 +52,22 @@ def main():
     pd, cd = torch.from_numpy(p).to(dev), torch.from_numpy(c).to(dev)
     backend = ofd.CudaBackend()
     times = []
+    plan = None
+    if args.driver == "peer":
+        plan = ofd.PeerRowbands(args.height, args.width, args.levels, 5, args.iters, mode)
     for _ in range(args.repeat + 1):  # first pass is warm-up
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ud, vd = ofd.lk_pyramidal_rowbands(pd, cd, args.levels, 5, args.iters, mode=mode, backend=backend, to_host=False)
+        if plan is not None:
+            ud, vd = plan.run(pd, cd)
+        else:
+            ud, vd = ofd.lk_pyramidal_rowbands(pd, cd, args.levels, 5, args.iters, mode=mode, backend=backend, to_host=False)
         torch.cuda.synchronize()
         dist.barrier()
         times.append(time.perf_counter() - t0)
+    if plan is not None:
+        plan.trace()  # raises if a peer wait timed out
     times = times[1:]
     u, v = ud.cpu().numpy(), vd.cpu().numpy()
     ok = None
@@ -84,7 +94,7 @@ def main():
     dist.destroy_process_group()
     if rank == 0:
         print(json.dumps({"world": world, "shape": [args.height, args.width], "levels": args.levels, "iters": args.iters,
-                          "mode": args.mode, "bit_equal_to_single_gpu": ok, "rowband_device_resident_s": min(times),
+                          "mode": args.mode, "driver": args.driver, "bit_equal_to_single_gpu": ok, "rowband_device_resident_s": min(times),
                           "single_gpu_device_resident_s": t_single,
                           "mpixel_per_s_rowband": args.height * args.width / min(times) / 1e6}))
         assert ok

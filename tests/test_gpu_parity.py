@@ -415,6 +415,50 @@ def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
     assert np.isnan(un[:10]).all() and np.isnan(un[37:]).all()  # rows outside the range untouched
 
 
+@pytest.mark.parametrize("mode_name", ["exact", "fast"])
+@pytest.mark.parametrize("world,shape,levels,iters", [(1, (200, 248), 3, 3), (3, (200, 248), 3, 3), (4, (270, 480), 4, 4),
+                                                      (8, (96, 128), 2, 2)])
+def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iters, mode_name):
+    """of_rowband_run: `world` ranks emulated on ONE device, each with its own arena and stream;
+    the peer "mapping" is the other contexts' arena pointers.  Every call only enqueues, so one
+    host thread can issue all ranks; the ranks' kernels then meet through the flag words exactly as
+    they do over NVLink.  Every rank's gathered flow must equal the whole-frame run bit for bit,
+    with the same early-exit decisions."""
+    import torch
+
+    import synthetic
+
+    mode = ofb.MODE_EXACT if mode_name == "exact" else ofb.MODE_FAST
+    H, W = shape
+    prev, curr, _ = synthetic.make_pairs_numpy(1, H, W, seed=31)
+    p, c = prev[0], np.roll(curr[0], 3, axis=0)
+    u1, v1, (iters_exec, _) = ofb.lk_pyramidal(p, c, levels, 5, iters, mode=mode, return_trace=True)
+    dev = torch.device("cuda", 0)
+    pd, cd = torch.from_numpy(p).to(dev), torch.from_numpy(c).to(dev)
+    ctxs = [ofb.RowbandContext(r, world, H, W, levels, 5, iters, mode) for r in range(world)]
+    try:
+        arenas = [cx.arena_ptr for cx in ctxs]
+        for cx in ctxs:
+            cx.set_peers(arenas)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(world)]  # non-blocking streams
+        torch.cuda.synchronize()
+        for rep in range(2):  # the second run reuses the arenas and the flag sequence numbers
+            outs = []
+            for r, cx in enumerate(ctxs):
+                uo, vo = torch.empty_like(pd), torch.empty_like(pd)
+                cx.run(pd.data_ptr(), cd.data_ptr(), uo.data_ptr(), vo.data_ptr(), streams[r].cuda_stream)
+                outs.append((uo, vo))
+            for r, cx in enumerate(ctxs):
+                it_r, _, err = cx.trace(streams[r].cuda_stream)
+                assert err == 0, f"rank {r}: a wait timed out"
+                assert it_r.tolist() == np.asarray(iters_exec).reshape(-1).tolist(), (r, it_r, iters_exec)
+                assert_bit_equal(outs[r][0].cpu().numpy(), u1, f"rank {r} u ({mode_name}, run {rep})")
+                assert_bit_equal(outs[r][1].cpu().numpy(), v1, f"rank {r} v ({mode_name}, run {rep})")
+    finally:
+        for cx in ctxs:
+            cx.close()
+
+
 @pytest.mark.parametrize("shape", [(16, 248), (135, 249), (300, 517), (333, 1000), (1080, 1920)])
 def test_pyramid_marching_kernel_against_oracle(ofb, shape):
     """One pyramid level by the marching kernel (frames >= 16 x 248) on general floats, odd sizes,
