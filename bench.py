@@ -269,7 +269,8 @@ def workload_config(name: str, wl: dict) -> dict:
         "mode": {"exact": "exact (reference operation order)", "fixed": "fixed-point S8.7 (RTL datapath)"}.get(wl.get("variant"), "fast"),
         "l2": "per-step inputs + outputs are far larger than the 126 MB L2, so no flush between iterations",
         "parallelism": ("each pair split into row bands over all ranks: all-reduce of the residual sums per "
-                        "iteration, all-gather of the owned rows per level (NCCL)") if wl.get("rowband")
+                        "iteration, all-gather of the owned rows per level, both by peer stores + flag words inside "
+                        "the kernels over NVLink (OF_B200_ROWBAND=nccl: NCCL collectives from a Python loop)") if wl.get("rowband")
         else "independent frame pairs sharded by rank, no data-path collective",
     }
 
@@ -373,15 +374,37 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     elif rowband:
         import distributed as ofd
 
-        backend = ofd.CudaBackend()
-        comm = ofd.TorchDistComm()
+        rb_driver = os.environ.get("OF_B200_ROWBAND", "peer")  # "nccl": the Python-loop driver (A/B runs)
+        if rb_driver == "nccl":
+            backend = ofd.CudaBackend()
+            comm = ofd.TorchDistComm()
 
-        def step():
-            for b in range(B):
-                ub, vb = ofd.lk_pyramidal_rowbands(prev[b], curr[b], wl["levels"], WINDOW, wl["iters"],
-                                                   mode=of_b200.MODE_FAST, comm=comm, backend=backend, to_host=False)
-                u[b].copy_(ub)
-                v[b].copy_(vb)
+            def step():
+                for b in range(B):
+                    ub, vb = ofd.lk_pyramidal_rowbands(prev[b], curr[b], wl["levels"], WINDOW, wl["iters"],
+                                                       mode=of_b200.MODE_FAST, comm=comm, backend=backend, to_host=False)
+                    u[b].copy_(ub)
+                    v[b].copy_(vb)
+        else:
+            # native driver: one C call per pair enqueues everything; the ranks meet through peer
+            # memory inside the kernels.  The whole step is captured in a CUDA graph (the sequence
+            # numbers of the collectives come from a device-side run counter, so replays are valid).
+            plan = ofd.PeerRowbands(H, W, wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST)
+
+            def enqueue():
+                st = torch.cuda.current_stream().cuda_stream
+                for b in range(B):
+                    plan.ctx.run(prev[b].data_ptr(), curr[b].data_ptr(), u[b].data_ptr(), v[b].data_ptr(), st)
+
+            enqueue()  # first call: function attributes, driver entry points
+            torch.cuda.synchronize()
+            if os.environ.get("OF_B200_GRAPH", "1") == "1":
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    enqueue()
+                step = graph.replay
+            else:
+                step = enqueue
     elif wl["pyramidal"]:
         ws_bytes = of_b200.lk_pyramidal_workspace_bytes(B, H, W, wl["levels"], wl["iters"])
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -416,6 +439,14 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     torch.cuda.synchronize()
     sampler.stop()
     launches = of_b200.kernel_launches() - launches0
+    if rowband and os.environ.get("OF_B200_ROWBAND", "peer") != "nccl":
+        plan.trace()  # raises if a wait on a peer timed out
+        if os.environ.get("OF_B200_GRAPH", "1") == "1":
+            # graph replays do not pass through the library's launch counter: count one step's launches
+            l0 = of_b200.kernel_launches()
+            enqueue()
+            torch.cuda.synchronize()
+            launches = (of_b200.kernel_launches() - l0) * args.steps
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)

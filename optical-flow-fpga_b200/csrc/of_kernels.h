@@ -137,16 +137,21 @@ struct PeerView {
     size_t flag_off, xchg_off;   // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD]; double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
     int* err;                    // sticky error word in the local arena (a wait timed out)
     unsigned long long timeout_ns;
+    // sequence number of collective `op` of a run = *run_id * ops_per_run + op (run_id: device word)
+    const unsigned long long* run_id;
+    unsigned long long ops_per_run;
 };
+// first kernel of a run: ++*run_id
+cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_t stream);
 // rows of a plane (current ping-pong buffer: sel[0] ^ sel_xor ? src1 : src0) -> byte offset dst_off
 // of every rank's arena; `first` / `count` in elements
 cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
                                   size_t dst_off, size_t first, size_t count, bool skip_self, int* launches,
                                   cudaStream_t stream);
-// signal sequence number `seq` to every rank and wait for every rank's
-cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long seq, int* launches, cudaStream_t stream);
+// signal collective `op` of the current run to every rank and wait for every rank's
+cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long op, int* launches, cudaStream_t stream);
 // all-reduce of (sum|du|, sum|dv|) + the reference's convergence test + ping-pong flip, in one kernel
-cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long seq, const double* partial, int blocks,
+cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long op, const double* partial, int blocks,
                                          double n_pixels, int* sel, int* done, int* iters_executed, float* residuals,
                                          int iteration, int* launches, cudaStream_t stream);
 

@@ -26,14 +26,14 @@ struct RowbandCtx {
     double gw[2 * OF_MAX_GAUSS_RADIUS + 1];
     std::vector<int> h, w;
     // arena offsets (bytes)
-    size_t flag_off = 0, xchg_off = 0, err_off = 0, sel_off = 0, done_off = 0, itx_off = 0, resid_off = 0;
+    size_t flag_off = 0, xchg_off = 0, err_off = 0, run_off = 0, sel_off = 0, done_off = 0, itx_off = 0, resid_off = 0;
     std::vector<size_t> prev_off, curr_off, au_off, av_off, bu_off, bv_off, gu_off, gv_off;
     size_t warped_off = 0, partial_off = 0, total = 0;
     char* base = nullptr;
     char* peer[PEER_MAX_WORLD];
     bool ipc_opened[PEER_MAX_WORLD];
     bool peers_set = false;
-    unsigned long long seq = 0;
+    unsigned long long ops_per_run = 1;
     int device = 0;
 };
 
@@ -52,6 +52,8 @@ PeerView rb_view(const RowbandCtx& c) {
     pv.xchg_off = c.xchg_off;
     pv.err = reinterpret_cast<int*>(c.base + c.err_off);
     pv.timeout_ns = 4000000000ULL;  // 4 s: far beyond any step, short enough not to wedge the device
+    pv.run_id = reinterpret_cast<const unsigned long long*>(c.base + c.run_off);
+    pv.ops_per_run = c.ops_per_run;
     return pv;
 }
 
@@ -111,6 +113,10 @@ int of_rowband_create(of_rowband_t** out, int rank, int world, int height, int w
     c->flag_off = take(sizeof(unsigned long long) * PEER_SLOTS * PEER_MAX_WORLD);
     c->xchg_off = take(sizeof(double) * PEER_SLOTS * PEER_MAX_WORLD * 2);
     c->err_off = take(sizeof(int));
+    c->run_off = take(sizeof(unsigned long long));
+    // collectives per run: one barrier per coarser pyramid level, one all-reduce per iteration and
+    // level, one barrier per level's flow gather
+    c->ops_per_run = (unsigned long long)(levels - 1) + (unsigned long long)levels * iterations + levels + 1;
     c->sel_off = take(sizeof(int) * levels);
     c->done_off = take(sizeof(int) * levels);
     c->itx_off = take(sizeof(int) * levels);
@@ -215,6 +221,8 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
     float* resid = reinterpret_cast<float*>(c.base + c.resid_off);
     double* partial = reinterpret_cast<double*>(c.base + c.partial_off);
     const int L = c.L, iters = c.iters, world = c.world, rank = c.rank;
+    unsigned long long op = 0;  // index of the next collective of this run
+    OF_CUDA(launch_peer_begin_run(pv, &cnt.n, st));
 
     // per-run control words (not the flags / exchange slots: their sequence numbers keep growing)
     OF_CUDA(cudaMemsetAsync(c.base + c.sel_off, 0, c.resid_off + align_up(sizeof(float) * L * (iters > 0 ? iters : 1) * 2) - c.sel_off, st));
@@ -238,7 +246,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
             const size_t first = (size_t)a * c.w[k], count = (size_t)(b - a) * c.w[k];
             OF_CUDA(launch_peer_push_rows(pv, lp[k], nullptr, nullptr, 0, c.prev_off[k], first, count, true, &cnt.n, st));
             OF_CUDA(launch_peer_push_rows(pv, lc[k], nullptr, nullptr, 0, c.curr_off[k], first, count, true, &cnt.n, st));
-            OF_CUDA(launch_peer_sync(pv, ++c.seq, &cnt.n, st));
+            OF_CUDA(launch_peer_sync(pv, op++, &cnt.n, st));
         }
     }
 
@@ -319,7 +327,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
                     blocks = lk_tile_blocks_per_pair(hi - lo, w);
                 }
             }
-            OF_CUDA(launch_peer_allreduce_update(pv, ++c.seq, b > a ? partial : nullptr, blocks, (double)h * (double)w, sel_k,
+            OF_CUDA(launch_peer_allreduce_update(pv, op++, b > a ? partial : nullptr, blocks, (double)h * (double)w, sel_k,
                                                  done_k, itx + ref_level, resid + (size_t)ref_level * (iters > 0 ? iters : 1) * 2,
                                                  it, &cnt.n, st));
         }
@@ -327,7 +335,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         const size_t first = (size_t)a * w, count = (size_t)(b - a) * w;
         OF_CUDA(launch_peer_push_rows(pv, fu(k, 0), fu(k, 1), sel_k, start, c.gu_off[k], first, count, false, &cnt.n, st));
         OF_CUDA(launch_peer_push_rows(pv, fv(k, 0), fv(k, 1), sel_k, start, c.gv_off[k], first, count, false, &cnt.n, st));
-        if (world > 1) OF_CUDA(launch_peer_sync(pv, ++c.seq, &cnt.n, st));
+        if (world > 1) OF_CUDA(launch_peer_sync(pv, op++, &cnt.n, st));
     }
     if (u) {
         const size_t bytes = (size_t)c.H * c.W * sizeof(float);

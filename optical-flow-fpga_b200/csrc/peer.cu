@@ -97,18 +97,23 @@ struct SyncArgs {
     int world, rank;
     size_t flag_off;  // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD] in every arena
     size_t xchg_off;  // double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
-    unsigned long long seq;
+    // sequence number of this collective = *run_id * ops_per_run + op: the run counter lives in
+    // device memory (bumped by the first kernel of every run), so a captured CUDA graph of a run
+    // can be replayed and still produces fresh, growing sequence numbers
+    const unsigned long long* run_id;
+    unsigned long long ops_per_run, op;
     int* err;
     unsigned long long timeout_ns;
 };
 
 __global__ void __launch_bounds__(32) peer_sync_kernel(const SyncArgs a) {
     const int r = threadIdx.x;
-    const int slot = (int)(a.seq % PEER_SLOTS);
+    const unsigned long long seq = *a.run_id * a.ops_per_run + a.op;
+    const int slot = (int)(seq % PEER_SLOTS);
     if (r < a.world) {
         __threadfence_system();  // the rows pushed by the kernels before this one
-        st_release_sys(reinterpret_cast<unsigned long long*>(a.peer[r] + a.flag_off) + slot * PEER_MAX_WORLD + a.rank, a.seq);
-        wait_flag(reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.flag_off) + slot * PEER_MAX_WORLD + r, a.seq,
+        st_release_sys(reinterpret_cast<unsigned long long*>(a.peer[r] + a.flag_off) + slot * PEER_MAX_WORLD + a.rank, seq);
+        wait_flag(reinterpret_cast<const unsigned long long*>(a.peer[a.rank] + a.flag_off) + slot * PEER_MAX_WORLD + r, seq,
                   a.err, a.timeout_ns);
     }
 }
@@ -150,7 +155,8 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const Allred
         red[1][threadIdx.x >> 5] = sv;
     }
     __syncthreads();
-    const int r = threadIdx.x, slot = (int)(a.s.seq % PEER_SLOTS);
+    const unsigned long long seq = *a.s.run_id * a.s.ops_per_run + a.s.op;
+    const int r = threadIdx.x, slot = (int)(seq % PEER_SLOTS);
     if (r < a.s.world) {
         su = 0.0;
         sv = 0.0;
@@ -164,11 +170,11 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const Allred
         x[1] = sv;
         __threadfence_system();
         st_release_sys(reinterpret_cast<unsigned long long*>(a.s.peer[r] + a.s.flag_off) + slot * PEER_MAX_WORLD + a.s.rank,
-                       a.s.seq);
+                       seq);
         // collect rank r's contribution from the local arena
         const bool got = wait_flag(reinterpret_cast<const unsigned long long*>(a.s.peer[a.s.rank] + a.s.flag_off) +
                                        slot * PEER_MAX_WORLD + r,
-                                   a.s.seq, a.s.err, a.s.timeout_ns);
+                                   seq, a.s.err, a.s.timeout_ns);
         const double* y = reinterpret_cast<const double*>(a.s.peer[a.s.rank] + a.s.xchg_off) + ((size_t)slot * PEER_MAX_WORLD + r) * 2;
         tot[r][0] = got ? *reinterpret_cast<const volatile double*>(y) : 0.0;
         tot[r][1] = got ? *reinterpret_cast<const volatile double*>(y + 1) : 0.0;
@@ -200,13 +206,17 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const Allred
 
 }  // namespace
 
-static void fill_sync(SyncArgs& s, const PeerView& pv, unsigned long long seq) {
+__global__ void peer_bump_run_kernel(unsigned long long* run_id) { *run_id += 1; }
+
+static void fill_sync(SyncArgs& s, const PeerView& pv, unsigned long long op) {
     for (int r = 0; r < PEER_MAX_WORLD; ++r) s.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
     s.world = pv.world;
     s.rank = pv.rank;
     s.flag_off = pv.flag_off;
     s.xchg_off = pv.xchg_off;
-    s.seq = seq;
+    s.run_id = pv.run_id;
+    s.ops_per_run = pv.ops_per_run;
+    s.op = op;
     s.err = pv.err;
     s.timeout_ns = pv.timeout_ns;
 }
@@ -234,19 +244,25 @@ cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const f
     return cudaGetLastError();
 }
 
-cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long seq, int* launches, cudaStream_t stream) {
+cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_t stream) {
+    if (launches) *launches += 1;
+    peer_bump_run_kernel<<<1, 1, 0, stream>>>(const_cast<unsigned long long*>(pv.run_id));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long op, int* launches, cudaStream_t stream) {
     SyncArgs s;
-    fill_sync(s, pv, seq);
+    fill_sync(s, pv, op);
     if (launches) *launches += 1;
     peer_sync_kernel<<<1, 32, 0, stream>>>(s);
     return cudaGetLastError();
 }
 
-cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long seq, const double* partial, int blocks,
+cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long op, const double* partial, int blocks,
                                          double n_pixels, int* sel, int* done, int* iters_executed, float* residuals,
                                          int iteration, int* launches, cudaStream_t stream) {
     AllreduceArgs a;
-    fill_sync(a.s, pv, seq);
+    fill_sync(a.s, pv, op);
     a.partial = partial;
     a.blocks = blocks;
     a.n_pixels = n_pixels;
