@@ -168,6 +168,20 @@ int of_lk_convergence_update_dev(const double* sums, int batch, double n_pixels,
 int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
                               int batch, int height, int width, int flags, void* stream);
 
+/* ---- flow-field error metrics on the device ----------------------------------------------
+ * compute_all_metrics(u_pred, v_pred, u_true, v_true, mask) of python/flow_metrics.py:166-201 for a
+ * batch of flow fields, the mask being the verifier's rectangular test region
+ * (python/optical_flow_verifier.py:96-138): rows [y0, y1), columns [x0, x1).  u_true / v_true hold one
+ * constant ground-truth flow per pair.  metrics[pair] = {mae_u, mae_v, rmse, epe, aae (degrees)}.
+ * Per-pixel arithmetic is the reference's float32; the means are float64 sums (the reference's are
+ * float32 pairwise sums), so values agree to float32 rounding of a mean, not bit for bit. */
+size_t of_flow_metrics_workspace_bytes(int batch, int region_height, int region_width);
+int of_flow_metrics_f32_dev(const float* u, const float* v, const float* u_true, const float* v_true, int batch,
+                            int height, int width, int y0, int y1, int x0, int x1, double* metrics,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int of_flow_metrics_f32(const float* u, const float* v, const float* u_true, const float* v_true, int batch, int height,
+                        int width, int y0, int y1, int x0, int x1, double* metrics);
+
 /* ---- row-band multi-GPU mode of lucas_kanade_pyramidal, native driver ---------------------
  * One frame pair, the rows of every pyramid level split over `world` ranks (one process -- or
  * thread -- per GPU of one NVLink / NVSwitch domain).  The reference has no multi-device path;

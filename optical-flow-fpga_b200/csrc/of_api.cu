@@ -402,7 +402,12 @@ int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float
     const size_t plane = (size_t)height * width;
     // chunks of <= 128 MiB per array, three in flight: H2D of chunk i+1 and D2H of chunk i-1
     // overlap the kernel of chunk i (needs pinned host memory to actually overlap)
-    size_t per_chunk = (128u << 20) / (plane * sizeof(float));
+    static const size_t chunk_mib = [] {
+        const char* e = getenv("OF_B200_CHUNK_MB");  // experiments: pipeline granularity of the host path
+        const long v = e ? atol(e) : 0;
+        return (size_t)(v >= 1 && v <= 1024 ? v : 128);
+    }();
+    size_t per_chunk = (chunk_mib << 20) / (plane * sizeof(float));
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > (size_t)batch) per_chunk = batch;
     const size_t chunk_bytes = per_chunk * plane * sizeof(float);
@@ -812,6 +817,56 @@ int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, 
     OF_TRY(of_lk_single_scale_fx_dev(dp, dc, du, dv, batch, height, width, flags, st));
     OF_CUDA(cudaMemcpyAsync(u, du, n * 2, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaMemcpyAsync(v, dv, n * 2, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+size_t of_flow_metrics_workspace_bytes(int batch, int height, int width) {
+    if (batch < 1 || height < 1 || width < 1) return 0;
+    return align_up((size_t)batch * metrics_blocks_per_pair(height, width) * 6 * sizeof(double));
+}
+
+int of_flow_metrics_f32_dev(const float* u, const float* v, const float* u_true, const float* v_true, int batch, int height,
+                            int width, int y0, int y1, int x0, int x1, double* metrics, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    OF_TRY(check_frame(u, v, height, width));
+    if (!u_true || !v_true || !metrics) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
+    if (y0 < 0 || y1 > height || x0 < 0 || x1 > width || y0 >= y1 || x0 >= x1)
+        return fail(OF_ERR_INVALID_ARGUMENT, "empty or out-of-frame test region");
+    if (!workspace || workspace_bytes < of_flow_metrics_workspace_bytes(batch, y1 - y0, x1 - x0))
+        return fail(OF_ERR_INVALID_ARGUMENT, "workspace missing or too small");
+    OF_TRY(need_device());
+    Counter cnt;
+    OF_CUDA(launch_flow_metrics(u, v, u_true, v_true, batch, height, width, y0, y1, x0, x1, static_cast<double*>(workspace),
+                                metrics, &cnt.n, static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+int of_flow_metrics_f32(const float* u, const float* v, const float* u_true, const float* v_true, int batch, int height,
+                        int width, int y0, int y1, int x0, int x1, double* metrics) {
+    OF_TRY(check_frame(u, v, height, width));
+    if (!u_true || !v_true || !metrics) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    const size_t n = (size_t)batch * height * width * sizeof(float);
+    const size_t ws = of_flow_metrics_workspace_bytes(batch, height, width);
+    float *du, *dv, *dt;
+    double *dm, *dw;
+    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&du)));
+    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dv)));
+    OF_TRY(g_arena.get(2, (size_t)batch * 2 * sizeof(float), reinterpret_cast<void**>(&dt)));
+    OF_TRY(g_arena.get(3, (size_t)batch * 5 * sizeof(double), reinterpret_cast<void**>(&dm)));
+    OF_TRY(g_arena.get(4, ws, reinterpret_cast<void**>(&dw)));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(du, u, n, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(dv, v, n, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(dt, u_true, (size_t)batch * sizeof(float), cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(dt + batch, v_true, (size_t)batch * sizeof(float), cudaMemcpyHostToDevice, st));
+    OF_TRY(of_flow_metrics_f32_dev(du, dv, dt, dt + batch, batch, height, width, y0, y1, x0, x1, dm, dw, ws, st));
+    OF_CUDA(cudaMemcpyAsync(metrics, dm, (size_t)batch * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaStreamSynchronize(st));
     return OF_OK;
 }

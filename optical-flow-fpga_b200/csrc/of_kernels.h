@@ -155,6 +155,13 @@ cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long 
                                          double n_pixels, int* sel, int* done, int* iters_executed, float* residuals,
                                          int iteration, int* launches, cudaStream_t stream);
 
+// ---- flow-field error metrics over a rectangular test region (metrics.cu) ---------------
+int metrics_blocks_per_pair(int rows, int cols);
+// partial: [batch][metrics_blocks_per_pair][6] doubles; out: [batch][5] = mae_u, mae_v, rmse, epe, aae
+cudaError_t launch_flow_metrics(const float* u, const float* v, const float* u_true, const float* v_true, int batch, int H,
+                                int W, int y0, int y1, int x0, int x1, double* partial, double* out, int* launches,
+                                cudaStream_t stream);
+
 // ---- fixed-point mode (lk_fixed.cu) ----------------------------------------------------
 cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,
                             int mirror_avg_quirk, int* launches, cudaStream_t stream);

@@ -83,6 +83,9 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp],
     ),
+    "of_flow_metrics_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "of_flow_metrics_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
+    "of_flow_metrics_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "of_rowband_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "of_rowband_arena_bytes": (C.c_size_t, [_vp]),
     "of_rowband_arena": (_vp, [_vp]),
@@ -424,6 +427,53 @@ def lk_refine_dev(
 def lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, mirror_avg_quirk=True, stream=0):
     flags = FX_MIRROR_AVG_QUIRK if mirror_avg_quirk else 0
     _check(lib().of_lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, flags, stream))
+
+
+METRIC_NAMES = ("mae_u", "mae_v", "rmse", "epe", "aae")
+
+
+def verifier_test_region(shape, pattern_type: str, center_crop_size: int = 80):
+    """(y0, y1, x0, x1) of the verifier's test-region mask (optical_flow_verifier.py:96-138):
+    rotation / zoom / combined patterns -> central crop, translations -> frame minus a 10 px border."""
+    h, w = int(shape[0]), int(shape[1])
+    if "rotate" in pattern_type or "zoom" in pattern_type:
+        cy, cx, half = h // 2, w // 2, int(center_crop_size) // 2
+        return cy - half, cy + half, cx - half, cx + half
+    return 10, h - 10, 10, w - 10
+
+
+def flow_metrics_batch(u, v, u_true, v_true, region=None):
+    """compute_all_metrics (flow_metrics.py:166-201) for [B, H, W] flow stacks on the GPU.
+    u_true / v_true: one constant ground-truth flow per pair.  region = (y0, y1, x0, x1) or None
+    for the whole frame.  Returns a list of dicts with the reference's keys."""
+    uu = np.ascontiguousarray(u, dtype=np.float32)
+    vv = np.ascontiguousarray(v, dtype=np.float32)
+    if uu.ndim == 2:
+        uu, vv = uu[None], vv[None]
+    if uu.ndim != 3 or uu.shape != vv.shape:
+        raise ValueError("u and v must be [B, H, W] (or [H, W]) arrays of equal shape")
+    b, h, w = uu.shape
+    ut = np.ascontiguousarray(np.broadcast_to(np.asarray(u_true, dtype=np.float32), (b,)))
+    vt = np.ascontiguousarray(np.broadcast_to(np.asarray(v_true, dtype=np.float32), (b,)))
+    y0, y1, x0, x1 = (0, h, 0, w) if region is None else (int(r) for r in region)
+    out = np.zeros((b, 5), dtype=np.float64)
+    _check(lib().of_flow_metrics_f32(_ptr(uu), _ptr(vv), _ptr(ut), _ptr(vt), b, h, w, y0, y1, x0, x1, _ptr(out)))
+    return [dict(zip(METRIC_NAMES, (float(x) for x in row))) for row in out]
+
+
+def flow_metrics_workspace_bytes(batch, region_height, region_width) -> int:
+    return int(lib().of_flow_metrics_workspace_bytes(batch, region_height, region_width))
+
+
+def flow_metrics_dev(u_ptr, v_ptr, u_true_ptr, v_true_ptr, batch, height, width, region, metrics_ptr, workspace_ptr,
+                     workspace_bytes, stream=0):
+    y0, y1, x0, x1 = (int(r) for r in region)
+    _check(
+        lib().of_flow_metrics_f32_dev(
+            u_ptr, v_ptr, u_true_ptr, v_true_ptr, batch, height, width, y0, y1, x0, x1, metrics_ptr, workspace_ptr,
+            workspace_bytes, stream,
+        )
+    )
 
 
 IPC_HANDLE_BYTES = 64

@@ -415,6 +415,43 @@ def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
     assert np.isnan(un[:10]).all() and np.isnan(un[37:]).all()  # rows outside the range untouched
 
 
+def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_frames):
+    """of_flow_metrics_f32 (compute_all_metrics over the verifier's test region, on the device):
+    all 13 patterns in ONE batched call per method.  Against the reference's
+    verification_baseline.json: equal to 3 decimals (the north star's tolerance) and within 2e-6
+    relative (float64 instead of float32-pairwise means); same against the CPU oracle."""
+    names = list(golden_index["patterns"])
+    crop = golden_index["center_crop"]
+    for method, runner in (("single_scale", lambda p, c: ofb.lk_single_scale(p, c, 5, mode=ofb.MODE_EXACT)),
+                           ("pyramidal", lambda p, c: ofb.lk_pyramidal(p, c, 3, 5, 3, mode=ofb.MODE_EXACT))):
+        by_region = {}
+        for name in names:
+            p, c = (f.astype(np.float32) for f in golden_frames[name])
+            u, v = runner(p, c)
+            by_region.setdefault(ofb.verifier_test_region(p.shape, name, crop), []).append((name, u, v))
+        for region, items in by_region.items():
+            gts = [golden_index["patterns"][n]["ground_truth"] for n, _, _ in items]
+            got = ofb.flow_metrics_batch(np.stack([u for _, u, _ in items]), np.stack([v for _, _, v in items]),
+                                         [g["u"] for g in gts], [g["v"] for g in gts], region)
+            for (name, u, v), g, m in zip(items, gts, got):
+                mask = fm.test_region_mask(u.shape, name, crop)
+                y0, y1, x0, x1 = region
+                assert mask.sum() == (y1 - y0) * (x1 - x0) and mask[y0:y1, x0:x1].all(), name
+                want = fm.all_metrics(u, v, g["u"], g["v"], mask)
+                base = golden_index["patterns"][name]["verification_baseline"][method]
+                for k in ofb.METRIC_NAMES:
+                    assert m[k] == pytest.approx(want[k], rel=2e-6, abs=1e-6), (method, name, k)
+                    assert m[k] == pytest.approx(base[k], rel=2e-6, abs=1e-6), (method, name, k)
+                    assert round(m[k], 3) == round(base[k], 3), (method, name, k)
+    # whole-frame region, a single [H, W] field, and the argument checks
+    u = np.full((40, 50), 1.5, np.float32)
+    m = ofb.flow_metrics_batch(u, -u, 1.0, 0.0)[0]
+    assert m["mae_u"] == pytest.approx(0.5) and m["mae_v"] == pytest.approx(1.5)
+    assert m["epe"] == pytest.approx(np.sqrt(0.25 + 2.25), rel=1e-6) and m["rmse"] == pytest.approx(m["epe"], rel=1e-6)
+    with pytest.raises(ValueError):
+        ofb.flow_metrics_batch(u, u, 0.0, 0.0, region=(10, 10, 0, 5))
+
+
 @pytest.mark.parametrize("mode_name", ["exact", "fast"])
 @pytest.mark.parametrize("world,shape,levels,iters", [(1, (200, 248), 3, 3), (3, (200, 248), 3, 3), (4, (270, 480), 4, 4),
                                                       (8, (96, 128), 2, 2)])
