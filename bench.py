@@ -42,6 +42,10 @@ WORKLOADS = {
     # secondary modes of the single-scale path (device-resident only)
     "single_1080p_exact": dict(batch=64, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="exact"),
     "fixed_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="fixed"),
+    # uint8 ingest of the float path: same flow, 10 B/pixel instead of 16
+    "single_1080p_u8": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="u8"),
+    # the north star's "4K frame-pair batch": same pixel count per step as the default workload
+    "single_4k": dict(batch=64, H=2160, W=3840, pyramidal=False, levels=1, iters=1),
     # BASELINE config 5: few very large frames; with N > 1 GPUs every pair is split into row
     # bands over all ranks (strong scaling, NCCL all-reduce per iteration + all-gather per level)
     "pyramidal_8k": dict(batch=2, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True),
@@ -266,7 +270,8 @@ def workload_config(name: str, wl: dict) -> dict:
         "height": wl["H"],
         "width": wl["W"],
         "window": WINDOW,
-        "mode": {"exact": "exact (reference operation order)", "fixed": "fixed-point S8.7 (RTL datapath)"}.get(wl.get("variant"), "fast"),
+        "mode": {"exact": "exact (reference operation order)", "fixed": "fixed-point S8.7 (RTL datapath)",
+                 "u8": "fast, uint8 frames in"}.get(wl.get("variant"), "fast"),
         "l2": "per-step inputs + outputs are far larger than the 126 MB L2, so no flush between iterations",
         "parallelism": ("each pair split into row bands over all ranks: all-reduce of the residual sums per "
                         "iteration, all-gather of the owned rows per level, both by peer stores + flag words inside "
@@ -275,7 +280,7 @@ def workload_config(name: str, wl: dict) -> dict:
     }
 
 
-def measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier):
+def measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier, u8=False):
     """Same metric through the host-buffer C-ABI call (of_lk_single_scale_f32): every step copies
     the step's frames from pinned host memory to the device, runs the kernel and copies (u, v)
     back, inside the timed region.  If the host cannot pin four full batches, the e2e batch is
@@ -283,9 +288,10 @@ def measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barri
     B, H, W = wl["batch"], wl["H"], wl["W"]
     eb = B
     bufs = None
+    in_dtype = np.uint8 if u8 else np.float32
     while eb >= 1:
         try:
-            bufs = [of_b200.PinnedArray((eb, H, W)) for _ in range(4)]
+            bufs = [of_b200.PinnedArray((eb, H, W), in_dtype) for _ in range(2)] + [of_b200.PinnedArray((eb, H, W)) for _ in range(2)]
             break
         except Exception:
             bufs = None
@@ -298,15 +304,16 @@ def measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barri
                 "unavailable": "could not allocate pinned host buffers"}
     eb = int(ok_all[1].item())  # every rank uses the smallest batch any rank could pin
     hp, hc, hu, hv = (b.array[:eb] for b in bufs)
-    hp[...] = prev[:eb].cpu().numpy()
-    hc[...] = curr[:eb].cpu().numpy()
+    hp[...] = prev[:eb].cpu().numpy().astype(in_dtype)
+    hc[...] = curr[:eb].cpu().numpy().astype(in_dtype)
+    call = of_b200.lk_single_scale_u8_batch if u8 else of_b200.lk_single_scale_batch
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(2):  # warm-up: arena allocation, streams
-        of_b200.lk_single_scale_batch(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
+        call(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        of_b200.lk_single_scale_batch(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
+        call(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -318,12 +325,12 @@ def measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barri
     out = {
         "value": world * px / (e2e_ms * 1e-3) / 1e6,
         "unit": "Mpixel/s",
-        "h2d_bytes_per_step": 2 * px * 4,
+        "h2d_bytes_per_step": 2 * px * (1 if u8 else 4),
         "d2h_bytes_per_step": 2 * px * 4,
         "ms_per_step": e2e_ms,
         "steps": e2e_steps,
         "frame_pairs_per_step_per_gpu": eb,
-        "api": "of_lk_single_scale_f32 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams",
+        "api": ("of_lk_single_scale_u8" if u8 else "of_lk_single_scale_f32") + " (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams",
         "matches_device_run": same,
     }
     del hp, hc, hu, hv
@@ -367,6 +374,11 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
 
         def step():
             of_b200.lk_single_scale_fx_dev(p8.data_ptr(), c8.data_ptr(), u16.data_ptr(), v16.data_ptr(), B, H, W, True, stream)
+    elif variant == "u8":
+        p8, c8 = prev.to(torch.uint8), curr.to(torch.uint8)
+
+        def step():
+            of_b200.lk_single_scale_u8_dev(p8.data_ptr(), c8.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, WINDOW, stream)
     elif variant == "exact":
         def step():
             of_b200.lk_single_scale_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
@@ -502,8 +514,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
 
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
     e2e = None
-    if not wl["pyramidal"] and not args.no_e2e and variant is None:
-        e2e = measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier)
+    if not wl["pyramidal"] and not args.no_e2e and variant in (None, "u8"):
+        e2e = measure_e2e(args, wl, of_b200, torch, dist, world, dev, prev, curr, u, barrier, u8=(variant == "u8"))
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -----------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -530,7 +542,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         return
 
     peak, peak_src = hbm_peak()
-    bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else (6.0 if variant == "fixed" else 16.0)
+    bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else {"fixed": 6.0, "u8": 10.0}.get(variant, 16.0)
     kernel_ms = statistics.mean(per_step)
     achieved = bpp * pixels_per_step / (kernel_ms * 1e-3) / 1e9
     line = {
@@ -561,7 +573,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             "peak_source": peak_src,
             "algorithmic_bytes_per_pixel": bpp,
             "kernel": ("whole pyramidal step (all launches)" if wl["pyramidal"] else
-                       {"fixed": "lk_fixed_kernel", "exact": "lk_tile_kernel<SRC_FRAMES, 5>"}.get(variant, "lk_march_kernel<true, false> (one launch per step)")),
+                       {"fixed": "lk_fixed_kernel", "exact": "lk_tile_kernel<SRC_FRAMES, 5>", "u8": "lk_march_kernel<true, false, true> (uint8 frames)"}.get(variant, "lk_march_kernel<true, false> (one launch per step)")),
             "kernel_ms": kernel_ms,
             "frac_of_nominal_8TBs": achieved / 8000.0,
         },

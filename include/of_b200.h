@@ -168,6 +168,20 @@ int of_lk_convergence_update_dev(const double* sums, int batch, double n_pixels,
 int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v,
                               int batch, int height, int width, int flags, void* stream);
 
+/* ---- uint8 ingest ---------------------------------------------------------------------------
+ * The reference's frames are uint8 on disk (frame_00.bin raw bytes, frame_00.mem one hex byte per
+ * line: python/generate_test_suite.py:259-271) and are widened to float32 by the callers
+ * (python/lucas_kanade_reference.py:133-140, optical_flow_verifier.py:61-65) before
+ * lucas_kanade_single_scale.  These entry points take the bytes directly: same float32 result, bit
+ * for bit, with 10 instead of 16 bytes of HBM traffic per pixel in fast mode. */
+int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int height,
+                          int width, int window, int mode);
+/* device buffers; fast mode only; needs window 5, width % 16 == 0, 16-byte aligned planes */
+int of_lk_single_scale_u8_dev(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int height,
+                              int width, int window, void* stream);
+/* read one [height][width] uint8 frame from a .bin (raw) or .mem (hex lines) file into host memory */
+int of_load_frame_u8(const char* path, uint8_t* out, int height, int width);
+
 /* ---- flow-field error metrics on the device ----------------------------------------------
  * compute_all_metrics(u_pred, v_pred, u_true, v_true, mask) of python/flow_metrics.py:166-201 for a
  * batch of flow fields, the mask being the verifier's rectangular test region

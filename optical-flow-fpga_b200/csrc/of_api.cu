@@ -400,12 +400,12 @@ int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float
     OF_TRY(host_streams());
     Counter cnt;
     const size_t plane = (size_t)height * width;
-    // chunks of <= 128 MiB per array, three in flight: H2D of chunk i+1 and D2H of chunk i-1
+    // chunks of <= 64 MiB per array, three in flight: H2D of chunk i+1 and D2H of chunk i-1
     // overlap the kernel of chunk i (needs pinned host memory to actually overlap)
     static const size_t chunk_mib = [] {
         const char* e = getenv("OF_B200_CHUNK_MB");  // experiments: pipeline granularity of the host path
         const long v = e ? atol(e) : 0;
-        return (size_t)(v >= 1 && v <= 1024 ? v : 128);
+        return (size_t)(v >= 1 && v <= 1024 ? v : 64);
     }();
     size_t per_chunk = (chunk_mib << 20) / (plane * sizeof(float));
     if (per_chunk < 1) per_chunk = 1;
@@ -818,6 +818,110 @@ int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, 
     OF_CUDA(cudaMemcpyAsync(u, du, n * 2, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaMemcpyAsync(v, dv, n * 2, cudaMemcpyDeviceToHost, st));
     OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
+// ---- uint8 ingest (the reference's on-disk frame formats) -------------------------------------
+int of_lk_single_scale_u8_dev(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int height,
+                              int width, int window, void* stream) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    OF_TRY(check_window(window));
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    if (!lk_march_u8_supported(prev, curr, u, v, height, width, window))
+        return fail(OF_ERR_UNSUPPORTED,
+                    "the device-buffer uint8 entry point needs window 5, width % 16 == 0 and 16-byte aligned planes "
+                    "(of_lk_single_scale_u8 takes any frame)");
+    Counter cnt;
+    OF_CUDA(launch_lk_march_u8(prev, curr, u, v, batch, height, width, &cnt.n, static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int height, int width,
+                          int window, int mode) {
+    OF_TRY(check_frame(prev, curr, height, width));
+    OF_TRY(check_frame(u, v, height, width));
+    OF_TRY(check_window(window));
+    if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
+    if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch == 0) return OF_OK;
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    Counter cnt;
+    const size_t plane = (size_t)height * width;
+    size_t per_chunk = ((size_t)64 << 20) / (plane * sizeof(float));
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > (size_t)batch) per_chunk = batch;
+    const int n_chunks = (int)((batch + per_chunk - 1) / per_chunk);
+    const int slots = n_chunks < 3 ? n_chunks : 3;
+    // per slot: uint8 prev / curr, float u / v, and (fallback only) float prev / curr
+    uint8_t* d8[3][2];
+    float* df[3][4];
+    for (int s = 0; s < slots; ++s) {
+        for (int j = 0; j < 2; ++j) OF_TRY(g_arena.get(12 + s * 2 + j, per_chunk * plane, reinterpret_cast<void**>(&d8[s][j])));
+        for (int j = 0; j < 2; ++j)
+            OF_TRY(g_arena.get(s * 4 + 2 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][2 + j])));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % slots;
+        cudaStream_t st = g_streams[s];
+        const size_t b0 = (size_t)c * per_chunk;
+        const int nb = (int)((size_t)batch - b0 < per_chunk ? (size_t)batch - b0 : per_chunk);
+        OF_CUDA(cudaMemcpyAsync(d8[s][0], prev + b0 * plane, (size_t)nb * plane, cudaMemcpyHostToDevice, st));
+        OF_CUDA(cudaMemcpyAsync(d8[s][1], curr + b0 * plane, (size_t)nb * plane, cudaMemcpyHostToDevice, st));
+        if (mode == OF_MODE_FAST && lk_march_u8_supported(d8[s][0], d8[s][1], df[s][2], df[s][3], height, width, window)) {
+            OF_CUDA(launch_lk_march_u8(d8[s][0], d8[s][1], df[s][2], df[s][3], nb, height, width, &cnt.n, st));
+        } else {
+            for (int j = 0; j < 2; ++j) {
+                OF_TRY(g_arena.get(s * 4 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][j])));
+                OF_CUDA(launch_u8_to_f32(d8[s][j], df[s][j], (size_t)nb * plane, &cnt.n, st));
+            }
+            OF_TRY(single_scale_dev(df[s][0], df[s][1], df[s][2], df[s][3], nb, height, width, window, mode, st, cnt));
+        }
+        OF_CUDA(cudaMemcpyAsync(u + b0 * plane, df[s][2], (size_t)nb * plane * sizeof(float), cudaMemcpyDeviceToHost, st));
+        OF_CUDA(cudaMemcpyAsync(v + b0 * plane, df[s][3], (size_t)nb * plane * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(g_streams[s]));
+    return OF_OK;
+}
+
+/* frame_00.bin / frame_00.mem of generate_test_suite.py:259-271: raw bytes, or one two-digit hex
+ * byte per line (the RTL testbenches' $readmemh format).  Chosen by the file extension. */
+int of_load_frame_u8(const char* path, uint8_t* out, int height, int width) {
+    if (!path || !out || height < 1 || width < 1) return fail(OF_ERR_INVALID_ARGUMENT, "bad argument");
+    const size_t n = (size_t)height * width;
+    const std::string p(path);
+    const bool is_mem = p.size() >= 4 && p.compare(p.size() - 4, 4, ".mem") == 0;
+    FILE* f = fopen(path, is_mem ? "r" : "rb");
+    if (!f) return fail(OF_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path);
+    size_t got = 0;
+    if (!is_mem) {
+        got = fread(out, 1, n, f);
+        unsigned char extra;
+        if (got == n && fread(&extra, 1, 1, f) == 1) got = n + 1;  // longer than the frame
+    } else {
+        char line[256];
+        while (fgets(line, sizeof(line), f)) {
+            char* q = line;
+            while (*q == ' ' || *q == '\t') ++q;
+            if (*q == '\0' || *q == '\n' || *q == '\r' || (q[0] == '/' && q[1] == '/')) continue;  // blank / comment
+            char* end = nullptr;
+            const unsigned long val = strtoul(q, &end, 16);
+            if (end == q || val > 255) {
+                fclose(f);
+                return fail(OF_ERR_INVALID_ARGUMENT, std::string("not a hex byte in ") + path + ": " + line);
+            }
+            if (got < n) out[got] = (uint8_t)val;
+            ++got;
+        }
+    }
+    fclose(f);
+    if (got != n)
+        return fail(OF_ERR_INVALID_ARGUMENT, std::string(path) + ": holds " + std::to_string(got) + " pixels, expected " +
+                                                 std::to_string(n));
     return OF_OK;
 }
 

@@ -31,6 +31,12 @@ bool lk_march_supported(int H, int W, int window);
 cudaError_t launch_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W,
                             int force_path, int* launches, cudaStream_t stream);
 
+// uint8 ingest of the same kernel (10 B per pixel): needs W % 16 == 0 and 16-byte aligned planes
+bool lk_march_u8_supported(const uint8_t* prev, const uint8_t* curr, const float* u, const float* v, int H, int W, int window);
+cudaError_t launch_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int H, int W,
+                               int* launches, cudaStream_t stream);
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, int* launches, cudaStream_t stream);
+
 // ---- K3 fast: warp-marching refinement iteration (lk_march.cu) --------------------------
 struct RefineArgs {
     const float* prev;  // level image of the previous frame   [B][H][W]

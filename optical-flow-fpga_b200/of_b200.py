@@ -83,6 +83,9 @@ SIGNATURES = {
         _i,
         [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp],
     ),
+    "of_lk_single_scale_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
+    "of_lk_single_scale_u8_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "of_load_frame_u8": (_i, [C.c_char_p, _vp, _i, _i]),
     "of_flow_metrics_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "of_flow_metrics_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "of_flow_metrics_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -427,6 +430,33 @@ def lk_refine_dev(
 def lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, mirror_avg_quirk=True, stream=0):
     flags = FX_MIRROR_AVG_QUIRK if mirror_avg_quirk else 0
     _check(lib().of_lk_single_scale_fx_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, flags, stream))
+
+
+def lk_single_scale_u8_batch(prev_u8, curr_u8, window_size: int = 5, mode: Optional[int] = None, out=None):
+    """lucas_kanade_single_scale on [B, H, W] uint8 frame stacks (the on-disk value range): the same
+    float32 flow as widening the frames first, with the widening done in registers on the GPU."""
+    p = np.ascontiguousarray(prev_u8)
+    c = np.ascontiguousarray(curr_u8)
+    if p.dtype != np.uint8 or c.dtype != np.uint8:
+        raise ValueError("frames must be uint8")
+    if p.ndim != 3 or p.shape != c.shape:
+        raise ValueError("prev and curr must be [B, H, W] arrays of equal shape")
+    b, h, w = p.shape
+    u, v = out if out is not None else (np.empty((b, h, w), np.float32), np.empty((b, h, w), np.float32))
+    m = default_mode() if mode is None else int(mode)
+    _check(lib().of_lk_single_scale_u8(_ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, _window(window_size), m))
+    return u, v
+
+
+def lk_single_scale_u8_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, window_size=5, stream=0):
+    _check(lib().of_lk_single_scale_u8_dev(prev_ptr, curr_ptr, u_ptr, v_ptr, batch, height, width, _window(window_size), stream))
+
+
+def load_frame_u8(path, height: int, width: int) -> np.ndarray:
+    """frame_XX.bin (raw bytes) or frame_XX.mem (one hex byte per line) -> uint8 [H, W]."""
+    out = np.empty((int(height), int(width)), np.uint8)
+    _check(lib().of_load_frame_u8(str(path).encode(), _ptr(out), int(height), int(width)))
+    return out
 
 
 METRIC_NAMES = ("mae_u", "mae_v", "rmse", "epe", "aae")

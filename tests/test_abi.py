@@ -138,3 +138,26 @@ def test_flow_field_text_export_format(of_b200, tmp_path):
     assert lines[4] == "0 0 0.000000 -0.000000" or lines[4] == "0 0 0.000000 0.000000"
     assert lines[-1] == "2 1 1.250000 -1.250000"
     assert len(lines) == 4 + 6
+
+
+def test_frame_loader_reads_the_reference_on_disk_formats(of_b200, tmp_path):
+    """of_load_frame_u8: frame_XX.bin is `ndarray.tofile` of uint8, frame_XX.mem is one `{val:02x}`
+    line per pixel (python/generate_test_suite.py:259-271).  Host-side I/O: runs without a GPU."""
+    fr = np.random.default_rng(3).integers(0, 256, (24, 40)).astype(np.uint8)
+    fr.tofile(tmp_path / "frame_00.bin")
+    with open(tmp_path / "frame_00.mem", "w") as f:
+        for val in fr.flatten():
+            f.write(f"{val:02x}\n")
+    assert np.array_equal(of_b200.load_frame_u8(tmp_path / "frame_00.bin", 24, 40), fr)
+    assert np.array_equal(of_b200.load_frame_u8(tmp_path / "frame_00.mem", 24, 40), fr)
+    (tmp_path / "c.mem").write_text("// comment\n\nff\n 0A\n")
+    assert of_b200.load_frame_u8(tmp_path / "c.mem", 1, 2).tolist() == [[255, 10]]
+    for shape in ((23, 40), (25, 40)):  # truncated / oversized files are errors, not partial frames
+        for name in ("frame_00.bin", "frame_00.mem"):
+            with pytest.raises(ValueError):
+                of_b200.load_frame_u8(tmp_path / name, *shape)
+    (tmp_path / "bad.mem").write_text("zz\n")
+    with pytest.raises(ValueError):
+        of_b200.load_frame_u8(tmp_path / "bad.mem", 1, 1)
+    with pytest.raises(ValueError):
+        of_b200.load_frame_u8(tmp_path / "missing.bin", 1, 1)

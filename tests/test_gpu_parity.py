@@ -415,6 +415,47 @@ def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
     assert np.isnan(un[:10]).all() and np.isnan(un[37:]).all()  # rows outside the range untouched
 
 
+@pytest.mark.parametrize("shape", [(240, 320), (64, 128), (37, 48), (1080, 1920), (50, 100), (33, 8)])
+def test_uint8_ingest_equals_float_path(ofb, shape, golden_index, golden_frames):
+    """of_lk_single_scale_u8: uint8 frames in, the float path's flow out, bit for bit -- through the
+    TMA uint8 kernel where the frame allows it (width % 16 == 0), through widening + the float
+    kernels elsewhere, in both modes; and equal to the oracle."""
+    import torch
+
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    if shape == (240, 320):
+        p8, c8 = golden_frames["translate_medium"]
+        p8, c8 = np.stack([p8, golden_frames["rotate_small"][0]]), np.stack([c8, golden_frames["rotate_small"][1]])
+    else:
+        p8 = rng.integers(0, 256, (3, H, W)).astype(np.uint8)
+        c8 = np.clip(np.roll(p8, 1, axis=2).astype(np.int32) + rng.integers(-3, 4, p8.shape), 0, 255).astype(np.uint8)
+    pf, cf = p8.astype(np.float32), c8.astype(np.float32)
+    for mode in (ofb.MODE_FAST, ofb.MODE_EXACT):
+        uf, vf = ofb.lk_single_scale_batch(pf, cf, 5, mode)
+        u8_, v8_ = ofb.lk_single_scale_u8_batch(p8, c8, 5, mode)
+        assert_bit_equal(u8_, uf, f"u ({shape}, mode {mode})")
+        assert_bit_equal(v8_, vf, f"v ({shape}, mode {mode})")
+    uo, vo = orc.lucas_kanade_single_scale(pf[0], cf[0], 5)
+    assert_bit_equal(u8_[0], uo, "u vs oracle")
+    assert_bit_equal(v8_[0], vo, "v vs oracle")
+    if shape == (240, 320):
+        assert sha(u8_[0]) == golden_index["patterns"]["translate_medium"]["single_scale"]["sha256_u"]
+    # device entry point: takes the TMA-able frames, refuses the others loudly
+    dev = torch.device("cuda", 0)
+    pd, cd = torch.from_numpy(p8).to(dev), torch.from_numpy(c8).to(dev)
+    ud = torch.empty(p8.shape, dtype=torch.float32, device=dev)
+    vd = torch.empty_like(ud)
+    if W % 16 == 0 and (H * W) % 16 == 0:
+        ofb.lk_single_scale_u8_dev(pd.data_ptr(), cd.data_ptr(), ud.data_ptr(), vd.data_ptr(), p8.shape[0], H, W)
+        torch.cuda.synchronize()
+        assert_bit_equal(ud.cpu().numpy(), uf, "dev u")
+        assert_bit_equal(vd.cpu().numpy(), vf, "dev v")
+    else:
+        with pytest.raises(ofb.OFBackendError):
+            ofb.lk_single_scale_u8_dev(pd.data_ptr(), cd.data_ptr(), ud.data_ptr(), vd.data_ptr(), p8.shape[0], H, W)
+
+
 def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_frames):
     """of_flow_metrics_f32 (compute_all_metrics over the verifier's test region, on the device):
     all 13 patterns in ONE batched call per method.  Against the reference's
