@@ -436,7 +436,7 @@ def test_uint8_ingest_equals_float_path(ofb, shape, golden_index, golden_frames)
         u8_, v8_ = ofb.lk_single_scale_u8_batch(p8, c8, 5, mode)
         assert_bit_equal(u8_, uf, f"u ({shape}, mode {mode})")
         assert_bit_equal(v8_, vf, f"v ({shape}, mode {mode})")
-    uo, vo = orc.lucas_kanade_single_scale(pf[0], cf[0], 5)
+    uo, vo = orc.lucas_kanade_single_scale(pf[0], cf[0], 5)  # u8_, v8_: the exact-mode run (last of the loop)
     assert_bit_equal(u8_[0], uo, "u vs oracle")
     assert_bit_equal(v8_[0], vo, "v vs oracle")
     if shape == (240, 320):
@@ -449,8 +449,9 @@ def test_uint8_ingest_equals_float_path(ofb, shape, golden_index, golden_frames)
     if W % 16 == 0 and (H * W) % 16 == 0:
         ofb.lk_single_scale_u8_dev(pd.data_ptr(), cd.data_ptr(), ud.data_ptr(), vd.data_ptr(), p8.shape[0], H, W)
         torch.cuda.synchronize()
-        assert_bit_equal(ud.cpu().numpy(), uf, "dev u")
-        assert_bit_equal(vd.cpu().numpy(), vf, "dev v")
+        uff, vff = ofb.lk_single_scale_batch(pf, cf, 5, ofb.MODE_FAST)  # random noise: fast != exact order
+        assert_bit_equal(ud.cpu().numpy(), uff, "dev u")
+        assert_bit_equal(vd.cpu().numpy(), vff, "dev v")
     else:
         with pytest.raises(ofb.OFBackendError):
             ofb.lk_single_scale_u8_dev(pd.data_ptr(), cd.data_ptr(), ud.data_ptr(), vd.data_ptr(), p8.shape[0], H, W)
