@@ -67,7 +67,7 @@ def hbm_peak():
 def ncu_traffic_bytes(workload: str, batch: int):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/), only when it was taken on this exact workload; else None."""
-    f = ROOT / "profiles" / "r01_lk_march_ncu_full_summary.json"
+    f = ROOT / "profiles" / "r01b_march_v2_ncu_full_summary.json"
     if workload != "single_1080p" or batch != 256 or not f.exists():
         return None
     try:
@@ -544,7 +544,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     peak, peak_src = hbm_peak()
     bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else {"fixed": 6.0, "u8": 10.0}.get(variant, 16.0)
     kernel_ms = statistics.mean(per_step)
-    achieved = bpp * pixels_per_step / (kernel_ms * 1e-3) / 1e9
+    # per-GPU figure: in row-band mode the ranks share the step's pixels
+    achieved = bpp * pixels_per_step / (world if rowband else 1) / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": "Mpixel/s",
         "value": value,
@@ -568,7 +569,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             "frac": achieved / peak,
             "traffic": ncu_traffic_bytes(args.workload, B),
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, "
-            "profiles/r01_lk_march_ncu_full_summary.json" if ncu_traffic_bytes(args.workload, B) else None,
+            "profiles/r01b_march_v2_ncu_full_summary.json" if ncu_traffic_bytes(args.workload, B) else None,
             "algorithmic_bytes": bpp * pixels_per_step,
             "peak_source": peak_src,
             "algorithmic_bytes_per_pixel": bpp,
