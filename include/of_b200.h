@@ -220,6 +220,10 @@ void* of_rowband_arena(const of_rowband_t* ctx); /* device pointer of this rank'
 int of_rowband_ipc_handle(const of_rowband_t* ctx, void* handle_out /* OF_IPC_HANDLE_BYTES */);
 int of_rowband_open_peers_ipc(of_rowband_t* ctx, const void* handles /* world x OF_IPC_HANDLE_BYTES, rank order */);
 int of_rowband_set_peers(of_rowband_t* ctx, void* const* arenas /* world device pointers, rank order */);
+/* Pyramid levels with at most `pixels` pixels are computed whole on every rank instead of in row
+ * bands (their kernels are launch-latency bound either way; replication removes their collectives).
+ * Default 600000; 0 = split every level.  Must be the same on every rank.  Same bits either way. */
+int of_rowband_set_replicate_pixels(of_rowband_t* ctx, long long pixels);
 /* prev, curr: the full [height][width] frames on this rank's device.  u, v: optional full-size
  * outputs (device); with NULL the result stays in the arena (of_rowband_result). */
 int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, float* u, float* v, void* stream);

@@ -35,6 +35,10 @@ struct RowbandCtx {
     bool peers_set = false;
     unsigned long long ops_per_run = 1;
     int device = 0;
+    // Levels with at most this many pixels are computed whole on every rank ("replicated"): their
+    // kernels are launch-latency bound at any band height, so splitting them buys nothing, while
+    // replication removes their collectives (no all-reduce per iteration, no gathers).
+    long long replicate_px = 600000;
 };
 
 void rb_shard(int n, int rank, int world, int* a, int* b) {
@@ -205,6 +209,12 @@ int of_rowband_set_peers(of_rowband_t* ctx, void* const* bases) {
     return OF_OK;
 }
 
+int of_rowband_set_replicate_pixels(of_rowband_t* ctx, long long pixels) {
+    if (!ctx || pixels < 0) return fail(OF_ERR_INVALID_ARGUMENT, "bad argument");
+    reinterpret_cast<RowbandCtx*>(ctx)->replicate_px = pixels;
+    return OF_OK;
+}
+
 int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, float* u, float* v, void* stream) {
     if (!ctx) return fail(OF_ERR_INVALID_ARGUMENT, "null context");
     RowbandCtx& c = *reinterpret_cast<RowbandCtx*>(ctx);
@@ -231,9 +241,18 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
     std::vector<const float*> lp(L), lc(L);
     lp[0] = prev;
     lc[0] = curr;
+    auto replicated = [&](int k) { return world > 1 && (long long)c.h[k] * c.w[k] <= c.replicate_px; };
+    PeerView pv_self = pv;  // "gather" of a replicated level: a local copy, no peers
+    pv_self.world = 1;
+    pv_self.rank = 0;
+    pv_self.peer[0] = c.base;
     for (int k = 1; k < L; ++k) {
         int a, b;
         rb_shard(c.h[k], rank, world, &a, &b);
+        if (replicated(k)) {
+            a = 0;
+            b = c.h[k];
+        }
         lp[k] = F(c.prev_off[k]);
         lc[k] = F(c.curr_off[k]);
         if (b > a) {
@@ -242,7 +261,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
             OF_CUDA(launch_pyramid_down(lc[k - 1], F(c.curr_off[k]), 1, c.h[k - 1], c.w[k - 1], c.h[k], c.w[k], c.gw, c.radius,
                                         a, b, &cnt.n, st));
         }
-        if (world > 1) {
+        if (world > 1 && !replicated(k)) {
             const size_t first = (size_t)a * c.w[k], count = (size_t)(b - a) * c.w[k];
             OF_CUDA(launch_peer_push_rows(pv, lp[k], nullptr, nullptr, 0, c.prev_off[k], first, count, true, &cnt.n, st));
             OF_CUDA(launch_peer_push_rows(pv, lc[k], nullptr, nullptr, 0, c.curr_off[k], first, count, true, &cnt.n, st));
@@ -264,13 +283,22 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         const int ref_level = kc - k;  // the reference counts levels from the coarsest
         int a, b;
         rb_shard(h, rank, world, &a, &b);
+        const bool repl = replicated(k);
+        if (repl) {
+            a = 0;
+            b = h;
+        }
         int* sel_k = sel + k;
         int* done_k = done + k;
         if (k < kc && b > a) {
             const int reach = RB_GROW * (iters > 1 ? iters : 1) + RB_GROW;
             const int lo = a - reach < 0 ? 0 : a - reach, hi = b + reach > h ? h : b + reach;
-            OF_CUDA(launch_upsample_flow(F(c.gu_off[k + 1]), F(c.gv_off[k + 1]), nullptr, nullptr, nullptr, 0, fu(k, start),
-                                         fv(k, start), 1, c.h[k + 1], c.w[k + 1], h, w, lo, hi, &cnt.n, st));
+            if (replicated(k + 1))  // the coarser level lives whole in this rank's ping-pong buffers
+                OF_CUDA(launch_upsample_flow(fu(k + 1, 0), fv(k + 1, 0), fu(k + 1, 1), fv(k + 1, 1), sel + (k + 1), start,
+                                             fu(k, start), fv(k, start), 1, c.h[k + 1], c.w[k + 1], h, w, lo, hi, &cnt.n, st));
+            else
+                OF_CUDA(launch_upsample_flow(F(c.gu_off[k + 1]), F(c.gv_off[k + 1]), nullptr, nullptr, nullptr, 0,
+                                             fu(k, start), fv(k, start), 1, c.h[k + 1], c.w[k + 1], h, w, lo, hi, &cnt.n, st));
         }
         RefineArgs ra;
         memset(&ra, 0, sizeof(ra));
@@ -327,15 +355,39 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
                     blocks = lk_tile_blocks_per_pair(hi - lo, w);
                 }
             }
-            OF_CUDA(launch_peer_allreduce_update(pv, op++, b > a ? partial : nullptr, blocks, (double)h * (double)w, sel_k,
-                                                 done_k, itx + ref_level, resid + (size_t)ref_level * (iters > 0 ? iters : 1) * 2,
-                                                 it, &cnt.n, st));
+            if (repl) {
+                // whole level on this rank: the single-GPU driver's convergence kernel, no exchange
+                IterFinalizeArgs f;
+                f.partial = partial;
+                f.blocks_per_pair = blocks;
+                f.H = h;
+                f.W = w;
+                f.sel = sel_k;
+                f.done = done_k;
+                f.iters_executed = itx + ref_level;
+                f.iters_pair_stride = L;
+                f.residuals = resid + (size_t)ref_level * (iters > 0 ? iters : 1) * 2;
+                f.resid_pair_stride = (size_t)L * (iters > 0 ? iters : 1) * 2;
+                f.iteration = it;
+                OF_CUDA(launch_iter_finalize(f, 1, &cnt.n, st));
+            } else {
+                OF_CUDA(launch_peer_allreduce_update(pv, op++, b > a ? partial : nullptr, blocks, (double)h * (double)w,
+                                                     sel_k, done_k, itx + ref_level,
+                                                     resid + (size_t)ref_level * (iters > 0 ? iters : 1) * 2, it, &cnt.n, st));
+            }
         }
         // level done: the owned rows of the current ping-pong buffer -> the gathered plane of every rank
+        // (a replicated level stays in its ping-pong buffers; only the finest one is copied, locally,
+        // to where of_rowband_result points)
         const size_t first = (size_t)a * w, count = (size_t)(b - a) * w;
-        OF_CUDA(launch_peer_push_rows(pv, fu(k, 0), fu(k, 1), sel_k, start, c.gu_off[k], first, count, false, &cnt.n, st));
-        OF_CUDA(launch_peer_push_rows(pv, fv(k, 0), fv(k, 1), sel_k, start, c.gv_off[k], first, count, false, &cnt.n, st));
-        if (world > 1) OF_CUDA(launch_peer_sync(pv, op++, &cnt.n, st));
+        if (!repl) {
+            OF_CUDA(launch_peer_push_rows(pv, fu(k, 0), fu(k, 1), sel_k, start, c.gu_off[k], first, count, false, &cnt.n, st));
+            OF_CUDA(launch_peer_push_rows(pv, fv(k, 0), fv(k, 1), sel_k, start, c.gv_off[k], first, count, false, &cnt.n, st));
+            if (world > 1) OF_CUDA(launch_peer_sync(pv, op++, &cnt.n, st));
+        } else if (k == 0) {
+            OF_CUDA(launch_peer_push_rows(pv_self, fu(k, 0), fu(k, 1), sel_k, start, c.gu_off[k], first, count, false, &cnt.n, st));
+            OF_CUDA(launch_peer_push_rows(pv_self, fv(k, 0), fv(k, 1), sel_k, start, c.gv_off[k], first, count, false, &cnt.n, st));
+        }
     }
     if (u) {
         const size_t bytes = (size_t)c.H * c.W * sizeof(float);

@@ -495,9 +495,10 @@ def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_f
 
 
 @pytest.mark.parametrize("mode_name", ["exact", "fast"])
-@pytest.mark.parametrize("world,shape,levels,iters", [(1, (200, 248), 3, 3), (3, (200, 248), 3, 3), (4, (270, 480), 4, 4),
-                                                      (8, (96, 128), 2, 2)])
-def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iters, mode_name):
+@pytest.mark.parametrize("world,shape,levels,iters,repl_px", [(1, (200, 248), 3, 3, 0), (3, (200, 248), 3, 3, 0),
+                                                              (4, (270, 480), 4, 4, 0), (4, (270, 480), 4, 4, 10000),
+                                                              (3, (200, 248), 3, 3, 10 ** 9), (8, (96, 128), 2, 2, 0)])
+def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iters, repl_px, mode_name):
     """of_rowband_run: `world` ranks emulated on ONE device, each with its own arena and stream;
     the peer "mapping" is the other contexts' arena pointers.  Every call only enqueues, so one
     host thread can issue all ranks; the ranks' kernels then meet through the flag words exactly as
@@ -519,6 +520,8 @@ def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iter
         arenas = [cx.arena_ptr for cx in ctxs]
         for cx in ctxs:
             cx.set_peers(arenas)
+            # 0: every level in row bands; 10000: the two coarsest levels whole on every rank; 1e9: all
+            cx.set_replicate_pixels(repl_px)
         streams = [torch.cuda.Stream(device=dev) for _ in range(world)]  # non-blocking streams
         torch.cuda.synchronize()
         for rep in range(2):  # the second run reuses the arenas and the flag sequence numbers
