@@ -480,6 +480,10 @@ class PeerRowbands:
         if mode is None:
             mode = of_b200.default_mode()
         self.ctx = of_b200.RowbandContext(self.rank, self.world, height, width, num_levels, window_size, num_iterations, mode)
+        import os
+
+        if os.environ.get("OF_B200_ROWBAND_REPL_PX"):  # A/B runs: 0 = split every level into row bands
+            self.ctx.set_replicate_pixels(int(os.environ["OF_B200_ROWBAND_REPL_PX"]))
         if self.world > 1:
             handles = [None] * self.world
             dist.all_gather_object(handles, self.ctx.ipc_handle())
