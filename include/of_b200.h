@@ -182,6 +182,26 @@ int of_lk_single_scale_u8_dev(const uint8_t* prev, const uint8_t* curr, float* u
 /* read one [height][width] uint8 frame from a .bin (raw) or .mem (hex lines) file into host memory */
 int of_load_frame_u8(const char* path, uint8_t* out, int height, int width);
 
+/* ---- flow-field text export (host-side I/O) --------------------------------------------------
+ * export_flow_field_txt of python/lucas_kanade_reference.py:78-103: header lines, then "x y u v" per
+ * pixel (row-major, six decimals) -- the format scripts/visualize_flow.py and the RTL testbench
+ * (tb/tb_optical_flow_top.sv:340-358) share.  x_min < 0: no "# Test region" line.  The _fx variant
+ * takes the fixed-point mode's S8.7 flow and writes the testbench's header. */
+int of_export_flow_txt(const char* path, const float* u, const float* v, int height, int width, int x_min, int x_max,
+                       int y_min, int y_max);
+int of_export_flow_fx_txt(const char* path, const int16_t* u, const int16_t* v, int height, int width, int x_min,
+                          int x_max, int y_min, int y_max);
+
+/* ---- apply_motion of the fixture generators -------------------------------------------------
+ * apply_motion(frame, dx, dy) of python/generate_test_frames_natural.py:67-73, i.e.
+ * scipy.ndimage.shift(frame, (dy, dx), order=1, mode="constant", cval=128) on uint8 frames, for a batch
+ * with one (dx, dy) per frame; bit-identical to SciPy.  Produces the second frame of a synthetic pair
+ * on the device.  dx / dy: [batch] float64 (host pointers for the host call, device pointers for _dev). */
+int of_apply_motion_u8(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* dx,
+                       const double* dy, double cval);
+int of_apply_motion_u8_dev(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* dx,
+                           const double* dy, double cval, void* stream);
+
 /* ---- flow-field error metrics on the device ----------------------------------------------
  * compute_all_metrics(u_pred, v_pred, u_true, v_true, mask) of python/flow_metrics.py:166-201 for a
  * batch of flow fields, the mask being the verifier's rectangular test region

@@ -925,6 +925,83 @@ int of_load_frame_u8(const char* path, uint8_t* out, int height, int width) {
     return OF_OK;
 }
 
+// ---- flow-field text export ---------------------------------------------------------------------
+static int export_flow_common(const char* path, const char* title, int height, int width, int x_min, int x_max, int y_min,
+                              int y_max, const float* u, const float* v, const int16_t* u_fx, const int16_t* v_fx) {
+    if (!path || height < 1 || width < 1) return fail(OF_ERR_INVALID_ARGUMENT, "bad argument");
+    FILE* f = fopen(path, "w");
+    if (!f) return fail(OF_ERR_INVALID_ARGUMENT, std::string("cannot open ") + path + " for writing");
+    std::vector<char> buf(1 << 20);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    fprintf(f, "%s\n# Format: x y u v\n# Image size: %dx%d\n", title, width, height);
+    if (x_min >= 0) fprintf(f, "# Test region: x[%d:%d], y[%d:%d]\n", x_min, x_max, y_min, y_max);
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            const size_t o = (size_t)y * width + x;
+            const double uu = u ? (double)u[o] : (double)u_fx[o] / 128.0;  // S8.7 -> pixels
+            const double vv = v ? (double)v[o] : (double)v_fx[o] / 128.0;
+            fprintf(f, "%d %d %.6f %.6f\n", x, y, uu, vv);
+        }
+    const bool bad = ferror(f) != 0;
+    if (fclose(f) != 0 || bad) return fail(OF_ERR_INVALID_ARGUMENT, std::string("write error on ") + path);
+    return OF_OK;
+}
+
+/* export_flow_field_txt (python/lucas_kanade_reference.py:78-103): "# ..." header lines, then one
+ * "x y u v" line per pixel, row-major, six decimals -- the file scripts/visualize_flow.py reads. */
+int of_export_flow_txt(const char* path, const float* u, const float* v, int height, int width, int x_min, int x_max,
+                       int y_min, int y_max) {
+    if (!u || !v) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    return export_flow_common(path, "# Optical flow field data (Python reference)", height, width, x_min, x_max, y_min, y_max,
+                              u, v, nullptr, nullptr);
+}
+
+/* The same file from the fixed-point mode's S8.7 flow, with the header the RTL testbench writes
+ * (tb/tb_optical_flow_top.sv:340-358), so a simulator dump can be diffed against it line by line. */
+int of_export_flow_fx_txt(const char* path, const int16_t* u, const int16_t* v, int height, int width, int x_min, int x_max,
+                          int y_min, int y_max) {
+    if (!u || !v) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    return export_flow_common(path, "# Optical flow field data", height, width, x_min, x_max, y_min, y_max, nullptr, nullptr,
+                              u, v);
+}
+
+// ---- apply_motion (fixture generators) ---------------------------------------------------------
+int of_apply_motion_u8_dev(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* dx,
+                           const double* dy, double cval, void* stream) {
+    OF_TRY(check_frame(frames, out, height, width));
+    if (!dx || !dy) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (frames == out) return fail(OF_ERR_INVALID_ARGUMENT, "in-place shifting is not supported");
+    if (batch < 1 || batch > 65535 || height > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch and height must be in 1..65535");
+    OF_TRY(need_device());
+    Counter cnt;
+    OF_CUDA(launch_apply_motion(frames, out, dx, dy, batch, height, width, cval, &cnt.n, static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+int of_apply_motion_u8(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* dx,
+                       const double* dy, double cval) {
+    OF_TRY(check_frame(frames, out, height, width));
+    if (!dx || !dy) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > 65535 || height > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch and height must be in 1..65535");
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    const size_t n = (size_t)batch * height * width;
+    uint8_t *ds, *dd;
+    double* dsh;
+    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&ds)));
+    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dd)));
+    OF_TRY(g_arena.get(2, (size_t)batch * 2 * sizeof(double), reinterpret_cast<void**>(&dsh)));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(ds, frames, n, cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(dsh, dx, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, st));
+    OF_CUDA(cudaMemcpyAsync(dsh + batch, dy, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, st));
+    OF_TRY(of_apply_motion_u8_dev(ds, dd, batch, height, width, dsh, dsh + batch, cval, st));
+    OF_CUDA(cudaMemcpyAsync(out, dd, n, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
 size_t of_flow_metrics_workspace_bytes(int batch, int height, int width) {
     if (batch < 1 || height < 1 || width < 1) return 0;
     return align_up((size_t)batch * metrics_blocks_per_pair(height, width) * 6 * sizeof(double));

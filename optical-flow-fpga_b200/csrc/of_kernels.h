@@ -4,7 +4,26 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace ofb {
+
+// Opt-in to more than 48 KB of dynamic shared memory, once per (kernel, device): the attribute
+// belongs to the device's context, so a process that drives several GPUs sets it on each.
+struct SmemOptIn {
+    std::atomic<unsigned long long> done{0};  // one bit per device ordinal
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kernel, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const unsigned long long bit = dev < 64 ? 1ULL << dev : 0ULL;
+        if (bit && (done.load(std::memory_order_relaxed) & bit)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_relaxed);
+        return e;
+    }
+};
 
 // ---- K1 fast: warp-marching fused single-scale LK (lk_march.cu) ------------------------
 struct MarchArgs {
@@ -167,6 +186,10 @@ int metrics_blocks_per_pair(int rows, int cols);
 cudaError_t launch_flow_metrics(const float* u, const float* v, const float* u_true, const float* v_true, int batch, int H,
                                 int W, int y0, int y1, int x0, int x1, double* partial, double* out, int* launches,
                                 cudaStream_t stream);
+
+// ---- fixture generators' sub-pixel shift (motion.cu) ------------------------------------
+cudaError_t launch_apply_motion(const uint8_t* src, uint8_t* dst, const double* dx, const double* dy, int batch, int H,
+                                int W, double cval, int* launches, cudaStream_t stream);
 
 // ---- fixed-point mode (lk_fixed.cu) ----------------------------------------------------
 cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,

@@ -251,13 +251,14 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
     const int IHmax = PYR_RMAX + 2 * radius, IWmax = PYR_CMAX + 2 * radius;
     const size_t smem =
         (size_t)((IHmax + PYR_SEG) * IWmax + PYR_RMAX * (IWmax + PYR_SEG + 1) + PYR_RMAX * (PYR_CMAX + 1)) * sizeof(float);
-    static size_t attr_smem[2] = {0, 0};
+    static SmemOptIn opt_in[2];
     const int which = radius == 8 ? 1 : 0;
-    if (smem > attr_smem[which]) {
-        cudaError_t e = which ? cudaFuncSetAttribute(pyramid_down_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : cudaFuncSetAttribute(pyramid_down_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        // the generic variant is opted in for its largest radius once, whatever radius comes first
+        const int IHcap = PYR_RMAX + 2 * PYR_MAX_RADIUS, IWcap = PYR_CMAX + 2 * PYR_MAX_RADIUS;
+        const size_t cap = (size_t)((IHcap + PYR_SEG) * IWcap + PYR_RMAX * (IWcap + PYR_SEG + 1) + PYR_RMAX * (PYR_CMAX + 1)) * sizeof(float);
+        cudaError_t e = which ? opt_in[1].ensure(pyramid_down_kernel<8>, smem) : opt_in[0].ensure(pyramid_down_kernel<0>, cap);
         if (e != cudaSuccess) return e;
-        attr_smem[which] = smem;
     }
     if (launches) *launches += 1;
     dim3 grid((ow + a.tile_w - 1) / a.tile_w, (row_hi - row_lo + a.tile_h - 1) / a.tile_h, batch);

@@ -239,11 +239,10 @@ cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H,
         }
     }
     const int n_bands = (rows + a.band_rows - 1) / a.band_rows;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pyramid_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM_BYTES);
+    static SmemOptIn opt_in;
+    {
+        cudaError_t e = opt_in.ensure(pyramid_march_kernel, PM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (launches) *launches += 1;
     dim3 grid(n_strips, n_bands, batch);

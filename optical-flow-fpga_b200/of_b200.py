@@ -86,6 +86,10 @@ SIGNATURES = {
     "of_lk_single_scale_u8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     "of_lk_single_scale_u8_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "of_load_frame_u8": (_i, [C.c_char_p, _vp, _i, _i]),
+    "of_export_flow_txt": (_i, [C.c_char_p, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "of_export_flow_fx_txt": (_i, [C.c_char_p, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "of_apply_motion_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, C.c_double]),
+    "of_apply_motion_u8_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, C.c_double, _vp]),
     "of_flow_metrics_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "of_flow_metrics_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "of_flow_metrics_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -458,6 +462,47 @@ def load_frame_u8(path, height: int, width: int) -> np.ndarray:
     out = np.empty((int(height), int(width)), np.uint8)
     _check(lib().of_load_frame_u8(str(path).encode(), _ptr(out), int(height), int(width)))
     return out
+
+
+def export_flow_txt(path, u, v, test_region=None) -> None:
+    """export_flow_field_txt (lucas_kanade_reference.py:78-103) written by the native library.
+    float32 flow -> the Python reference's header; int16 S8.7 flow (fixed-point mode) -> the RTL
+    testbench's header.  test_region: dict with x_min / x_max / y_min / y_max, or None."""
+    uu, vv = np.ascontiguousarray(u), np.ascontiguousarray(v)
+    if uu.ndim != 2 or uu.shape != vv.shape or uu.dtype != vv.dtype:
+        raise ValueError("u and v must be 2-D arrays of equal shape and dtype")
+    h, w = uu.shape
+    r = test_region or {"x_min": -1, "x_max": -1, "y_min": -1, "y_max": -1}
+    args = (str(path).encode(), _ptr(uu), _ptr(vv), h, w, int(r["x_min"]), int(r["x_max"]), int(r["y_min"]), int(r["y_max"]))
+    if uu.dtype == np.float32:
+        _check(lib().of_export_flow_txt(*args))
+    elif uu.dtype == np.int16:
+        _check(lib().of_export_flow_fx_txt(*args))
+    else:
+        raise ValueError("flow must be float32 (pixels) or int16 (S8.7)")
+
+
+def apply_motion_u8_batch(frames_u8, dx, dy, cval: float = 128.0) -> np.ndarray:
+    """apply_motion (generate_test_frames_natural.py:67-73) for [B, H, W] (or [H, W]) uint8 frames with
+    one (dx, dy) per frame: scipy.ndimage.shift(..., order=1, mode="constant", cval) bit for bit."""
+    f = np.ascontiguousarray(frames_u8)
+    if f.dtype != np.uint8:
+        raise ValueError("frames must be uint8")
+    single = f.ndim == 2
+    if single:
+        f = f[None]
+    if f.ndim != 3:
+        raise ValueError("frames must be [B, H, W] or [H, W]")
+    b, h, w = f.shape
+    xs = np.ascontiguousarray(np.broadcast_to(np.asarray(dx, dtype=np.float64), (b,)))
+    ys = np.ascontiguousarray(np.broadcast_to(np.asarray(dy, dtype=np.float64), (b,)))
+    out = np.empty_like(f)
+    _check(lib().of_apply_motion_u8(_ptr(f), _ptr(out), b, h, w, _ptr(xs), _ptr(ys), float(cval)))
+    return out[0] if single else out
+
+
+def apply_motion_u8_dev(frames_ptr, out_ptr, batch, height, width, dx_ptr, dy_ptr, cval: float = 128.0, stream=0):
+    _check(lib().of_apply_motion_u8_dev(frames_ptr, out_ptr, batch, height, width, dx_ptr, dy_ptr, float(cval), stream))
 
 
 METRIC_NAMES = ("mae_u", "mae_v", "rmse", "epe", "aae")

@@ -161,3 +161,34 @@ def test_frame_loader_reads_the_reference_on_disk_formats(of_b200, tmp_path):
         of_b200.load_frame_u8(tmp_path / "bad.mem", 1, 1)
     with pytest.raises(ValueError):
         of_b200.load_frame_u8(tmp_path / "missing.bin", 1, 1)
+
+
+def test_native_flow_export_matches_the_reference_format(of_b200, tmp_path):
+    """of_export_flow_txt writes what export_flow_field_txt (python/lucas_kanade_reference.py:78-103)
+    writes: same header, same "x y u v" lines with Python's "%.6f" rounding.  Host-side I/O."""
+    rng = np.random.default_rng(1)
+    u = (rng.standard_normal((7, 9)) * 3).astype(np.float32)
+    v = (rng.standard_normal((7, 9)) * 3).astype(np.float32)
+    u[0, 0], v[0, 0], u[1, 1] = 0.0, -0.0, np.float32(0.0000005)
+    region = {"x_min": 2, "x_max": 6, "y_min": 1, "y_max": 5}
+    for reg in (region, None):
+        want = ["# Optical flow field data (Python reference)", "# Format: x y u v", "# Image size: 9x7"]
+        if reg:
+            want.append("# Test region: x[2:6], y[1:5]")
+        for y in range(7):
+            for x in range(9):
+                want.append(f"{x} {y} {u[y, x]:.6f} {v[y, x]:.6f}")
+        of_b200.export_flow_txt(tmp_path / "flow.txt", u, v, reg)
+        assert (tmp_path / "flow.txt").read_text().splitlines() == want
+    import lucas_kanade_reference as ref_mod  # the drop-in module writes the same file
+
+    ref_mod.export_flow_field_txt(u, v, tmp_path / "flow_py.txt", 9, 7, region)
+    of_b200.export_flow_txt(tmp_path / "flow.txt", u, v, region)
+    assert (tmp_path / "flow_py.txt").read_text() == (tmp_path / "flow.txt").read_text()
+    fx = (rng.integers(-1024, 1025, (4, 5))).astype(np.int16)
+    of_b200.export_flow_txt(tmp_path / "fx.txt", fx, -fx)
+    lines = (tmp_path / "fx.txt").read_text().splitlines()
+    assert lines[0] == "# Optical flow field data" and lines[2] == "# Image size: 5x4"
+    assert lines[3] == f"0 0 {fx[0, 0] / 128:.6f} {-fx[0, 0] / 128:.6f}"
+    with pytest.raises(ValueError):
+        of_b200.export_flow_txt(tmp_path / "no_such_dir" / "f.txt", u, v)

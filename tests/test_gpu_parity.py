@@ -457,6 +457,29 @@ def test_uint8_ingest_equals_float_path(ofb, shape, golden_index, golden_frames)
             ofb.lk_single_scale_u8_dev(pd.data_ptr(), cd.data_ptr(), ud.data_ptr(), vd.data_ptr(), p8.shape[0], H, W)
 
 
+def test_apply_motion_kernel_equals_scipy_shift(ofb):
+    """of_apply_motion_u8 against the reference's apply_motion outputs (tests/golden/motion.npz) and,
+    on a batch with one random sub-pixel shift per frame, against the oracle."""
+    from conftest import GOLDEN
+    from oracle import pattern_oracle as po
+
+    z = np.load(GOLDEN / "motion.npz")
+    cases = z["cases"]
+    for name, src in (("texture", z["texture_128x96"]), ("noise", z["noise_53x37"])):
+        batch = np.repeat(src[None], len(cases), axis=0)
+        got = ofb.apply_motion_u8_batch(batch, cases[:, 0], cases[:, 1])
+        for i in range(len(cases)):
+            assert_bit_equal(got[i], z[f"{name}_shift_{i}"], f"{name} shift {cases[i].tolist()}")
+    rng = np.random.default_rng(9)
+    frames = rng.integers(0, 256, (6, 270, 481)).astype(np.uint8)
+    dx, dy = rng.uniform(-3, 3, 6), rng.uniform(-3, 3, 6)
+    got = ofb.apply_motion_u8_batch(frames, dx, dy)
+    for b in range(6):
+        assert_bit_equal(got[b], po.apply_motion(frames[b], dx[b], dy[b]), f"random shift {b}")
+    assert_bit_equal(ofb.apply_motion_u8_batch(frames[0], 0.0, 0.0), frames[0], "zero shift is the identity")
+    assert_bit_equal(ofb.apply_motion_u8_batch(frames[0], 1.5, 0.0, cval=7.0), po.apply_motion(frames[0], 1.5, 0.0, 7.0), "cval")
+
+
 def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_frames):
     """of_flow_metrics_f32 (compute_all_metrics over the verifier's test region, on the device):
     all 13 patterns in ONE batched call per method.  Against the reference's

@@ -125,3 +125,16 @@ def test_subset_full_arrays(golden_flows, golden_frames):
         us, vs = orc.lucas_kanade_single_scale(f0.astype(np.float32), f1.astype(np.float32))
         assert np.array_equal(us, golden_flows[f"{name}__single_u"])
         assert np.array_equal(vs, golden_flows[f"{name}__single_v"])
+
+
+def test_pattern_oracle_equals_reference_generators():
+    """oracle/pattern_oracle.py against tests/golden/motion.npz, which holds outputs of the
+    reference's own generate_smooth_synthetic and apply_motion (scipy.ndimage.shift)."""
+    from conftest import GOLDEN
+    from oracle import pattern_oracle as po
+
+    z = np.load(GOLDEN / "motion.npz")
+    assert np.array_equal(po.generate_smooth_synthetic(128, 96), z["texture_128x96"])
+    for i, (dx, dy) in enumerate(z["cases"]):
+        for name, src in (("texture", z["texture_128x96"]), ("noise", z["noise_53x37"])):
+            assert np.array_equal(po.apply_motion(src, dx, dy), z[f"{name}_shift_{i}"]), (name, dx, dy)
