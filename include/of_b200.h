@@ -244,6 +244,10 @@ int of_rowband_set_peers(of_rowband_t* ctx, void* const* arenas /* world device 
  * bands (their kernels are launch-latency bound either way; replication removes their collectives).
  * Default 600000; 0 = split every level.  Must be the same on every rank.  Same bits either way. */
 int of_rowband_set_replicate_pixels(of_rowband_t* ctx, long long pixels);
+/* How long a kernel spins on a peer's flag before it gives up, sets the error word (of_rowband_trace)
+ * and lets the run drain: default 4000 ms.  The ranks must enter of_rowband_run within this time of
+ * each other; raise it when one rank may be late (I/O), lower it to fail fast. */
+int of_rowband_set_timeout_ms(of_rowband_t* ctx, int milliseconds);
 /* prev, curr: the full [height][width] frames on this rank's device.  u, v: optional full-size
  * outputs (device); with NULL the result stays in the arena (of_rowband_result). */
 int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, float* u, float* v, void* stream);

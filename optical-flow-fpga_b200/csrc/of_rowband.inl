@@ -39,6 +39,10 @@ struct RowbandCtx {
     // kernels are launch-latency bound at any band height, so splitting them buys nothing, while
     // replication removes their collectives (no all-reduce per iteration, no gathers).
     long long replicate_px = 600000;
+    // how long a kernel waits for a peer before it gives up and sets the error word: far beyond any
+    // step, short enough that a dead peer does not wedge the device.  Ranks must therefore enter
+    // of_rowband_run within this time of each other.
+    unsigned long long timeout_ns = 4000000000ULL;
 };
 
 void rb_shard(int n, int rank, int world, int* a, int* b) {
@@ -55,7 +59,7 @@ PeerView rb_view(const RowbandCtx& c) {
     pv.flag_off = c.flag_off;
     pv.xchg_off = c.xchg_off;
     pv.err = reinterpret_cast<int*>(c.base + c.err_off);
-    pv.timeout_ns = 4000000000ULL;  // 4 s: far beyond any step, short enough not to wedge the device
+    pv.timeout_ns = c.timeout_ns;
     pv.run_id = reinterpret_cast<const unsigned long long*>(c.base + c.run_off);
     pv.ops_per_run = c.ops_per_run;
     return pv;
@@ -212,6 +216,12 @@ int of_rowband_set_peers(of_rowband_t* ctx, void* const* bases) {
 int of_rowband_set_replicate_pixels(of_rowband_t* ctx, long long pixels) {
     if (!ctx || pixels < 0) return fail(OF_ERR_INVALID_ARGUMENT, "bad argument");
     reinterpret_cast<RowbandCtx*>(ctx)->replicate_px = pixels;
+    return OF_OK;
+}
+
+int of_rowband_set_timeout_ms(of_rowband_t* ctx, int milliseconds) {
+    if (!ctx || milliseconds < 1 || milliseconds > 600000) return fail(OF_ERR_INVALID_ARGUMENT, "timeout must be in 1 ms .. 10 min");
+    reinterpret_cast<RowbandCtx*>(ctx)->timeout_ns = (unsigned long long)milliseconds * 1000000ULL;
     return OF_OK;
 }
 

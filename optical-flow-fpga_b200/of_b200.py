@@ -100,6 +100,7 @@ SIGNATURES = {
     "of_rowband_open_peers_ipc": (_i, [_vp, _vp]),
     "of_rowband_set_peers": (_i, [_vp, C.POINTER(_vp)]),
     "of_rowband_set_replicate_pixels": (_i, [_vp, C.c_longlong]),
+    "of_rowband_set_timeout_ms": (_i, [_vp, _i]),
     "of_rowband_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "of_rowband_result": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "of_rowband_trace": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -606,6 +607,10 @@ class RowbandContext:
     def set_replicate_pixels(self, pixels: int) -> None:
         """Levels of at most `pixels` pixels are computed whole on every rank (default 600000, 0 = never)."""
         _check(lib().of_rowband_set_replicate_pixels(self._ctx, int(pixels)))
+
+    def set_timeout_ms(self, milliseconds: int) -> None:
+        """Peer wait time-out (default 4000 ms); the ranks must enter run() within it of each other."""
+        _check(lib().of_rowband_set_timeout_ms(self._ctx, int(milliseconds)))
 
     def run(self, prev_ptr, curr_ptr, u_ptr=None, v_ptr=None, stream=0) -> None:
         _check(lib().of_rowband_run(self._ctx, prev_ptr, curr_ptr, u_ptr, v_ptr, stream))

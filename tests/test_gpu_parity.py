@@ -564,6 +564,36 @@ def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iter
             cx.close()
 
 
+def test_native_rowband_driver_times_out_instead_of_hanging(ofb):
+    """A rank whose peer never shows up must not wedge the GPU: every spin has a time-out that sets a
+    sticky error word, the run drains, and of_rowband_trace reports it."""
+    import time
+
+    import torch
+
+    import synthetic
+
+    H, W = 200, 248
+    prev, curr, _ = synthetic.make_pairs_numpy(1, H, W, seed=5)
+    dev = torch.device("cuda", 0)
+    pd, cd = torch.from_numpy(prev[0]).to(dev), torch.from_numpy(curr[0]).to(dev)
+    ctxs = [ofb.RowbandContext(r, 2, H, W, 3, 5, 3, ofb.MODE_FAST) for r in range(2)]
+    try:
+        for cx in ctxs:
+            cx.set_peers([c.arena_ptr for c in ctxs])
+            cx.set_replicate_pixels(0)
+            cx.set_timeout_ms(40)
+        st = torch.cuda.Stream(device=dev)
+        t0 = time.perf_counter()
+        ctxs[0].run(pd.data_ptr(), cd.data_ptr(), None, None, st.cuda_stream)  # rank 1 never runs
+        _, _, err = ctxs[0].trace(st.cuda_stream)
+        assert err == 1
+        assert time.perf_counter() - t0 < 5.0  # one time-out, then every later wait falls through
+    finally:
+        for cx in ctxs:
+            cx.close()
+
+
 @pytest.mark.parametrize("shape", [(16, 248), (135, 249), (300, 517), (333, 1000), (1080, 1920)])
 def test_pyramid_marching_kernel_against_oracle(ofb, shape):
     """One pyramid level by the marching kernel (frames >= 16 x 248) on general floats, odd sizes,
