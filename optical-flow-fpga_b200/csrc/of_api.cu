@@ -789,8 +789,18 @@ int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t*
     const size_t plane = (size_t)height * width;
     for (int b0 = 0; b0 < batch; b0 += 65535) {
         const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
-        OF_CUDA(launch_lk_fixed(prev + b0 * plane, curr + b0 * plane, u + b0 * plane, v + b0 * plane, nb, height, width,
-                                (flags & OF_FX_MIRROR_AVG_QUIRK) ? 1 : 0, &cnt.n, static_cast<cudaStream_t>(stream)));
+        // the marching kernel (TMA uint8 boxes: width % 16 == 0, 16-byte aligned planes); else the tile kernel
+        static const bool force_tile = [] {
+            const char* e = getenv("OF_B200_FIXED");
+            return e != nullptr && strcmp(e, "tile") == 0;  // A/B runs
+        }();
+        const int quirk = (flags & OF_FX_MIRROR_AVG_QUIRK) ? 1 : 0;
+        if (!force_tile && lk_march_fx_supported(prev + b0 * plane, curr + b0 * plane, u + b0 * plane, v + b0 * plane, height, width))
+            OF_CUDA(launch_lk_march_fx(prev + b0 * plane, curr + b0 * plane, u + b0 * plane, v + b0 * plane, nb, height,
+                                       width, quirk, &cnt.n, static_cast<cudaStream_t>(stream)));
+        else
+            OF_CUDA(launch_lk_fixed(prev + b0 * plane, curr + b0 * plane, u + b0 * plane, v + b0 * plane, nb, height, width,
+                                    quirk, &cnt.n, static_cast<cudaStream_t>(stream)));
     }
     return OF_OK;
 }

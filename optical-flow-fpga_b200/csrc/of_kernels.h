@@ -44,6 +44,10 @@ struct MarchArgs {
     const int* done;
     double* partial;
     int row_lo, row_hi, own_lo, own_hi;
+    // fixed-point flavour: int16 S8.7 outputs, and whether to mirror the 9-bit average of gradient_compute.sv:116
+    int16_t* u16;
+    int16_t* v16;
+    int fx_quirk;
 };
 bool lk_march_supported(int H, int W, int window);
 // force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
@@ -54,6 +58,10 @@ cudaError_t launch_lk_march(const float* prev, const float* curr, float* u, floa
 bool lk_march_u8_supported(const uint8_t* prev, const uint8_t* curr, const float* u, const float* v, int H, int W, int window);
 cudaError_t launch_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int H, int W,
                                int* launches, cudaStream_t stream);
+// the RTL's fixed-point datapath on the same marching kernel (6 B per pixel); same frame requirements
+bool lk_march_fx_supported(const uint8_t* prev, const uint8_t* curr, const int16_t* u, const int16_t* v, int H, int W);
+cudaError_t launch_lk_march_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,
+                               int mirror_avg_quirk, int* launches, cudaStream_t stream);
 cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, int* launches, cudaStream_t stream);
 
 // ---- K3 fast: warp-marching refinement iteration (lk_march.cu) --------------------------

@@ -334,6 +334,24 @@ def test_fixed_point_mode_bit_exact(ofb, golden_frames, quirk):
         assert_bit_equal(u[b], uo, f"random {b} u")
         assert_bit_equal(v[b], vo, f"random {b} v")
     assert np.abs(u).max() <= 1024 and np.abs(v).max() <= 1024
+    # worst-case contrast on frames the marching kernel takes (width % 16 == 0): 32-bit wraps of the
+    # 64-bit products, quotients that wrap in 16 bits, the +-8 px clamp; ragged heights, tiny frames
+    for shape in ((4, 64, 128), (2, 37, 48), (1, 7, 16), (1, 200, 256), (2, 9, 32)):
+        p = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        c = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        u, v = ofb.lk_single_scale_fx(p, c, mirror_avg_quirk=quirk)
+        for b in range(shape[0]):
+            uo, vo = fxo.lk_single_scale_fx(p[b], c[b], mirror_avg_quirk=quirk)
+            assert_bit_equal(u[b], uo, f"noise {shape} pair {b} u")
+            assert_bit_equal(v[b], vo, f"noise {shape} pair {b} v")
+    # low contrast: small determinants around the |det| > 1000 threshold
+    p = (128 + rng.integers(-3, 4, size=(2, 96, 160))).astype(np.uint8)
+    c = np.roll(p, 1, axis=2)
+    u, v = ofb.lk_single_scale_fx(p, c, mirror_avg_quirk=quirk)
+    for b in range(2):
+        uo, vo = fxo.lk_single_scale_fx(p[b], c[b], mirror_avg_quirk=quirk)
+        assert_bit_equal(u[b], uo, f"low contrast {b} u")
+        assert_bit_equal(v[b], vo, f"low contrast {b} v")
 
 
 def test_error_behaviour(ofb):
