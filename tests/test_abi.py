@@ -192,3 +192,17 @@ def test_native_flow_export_matches_the_reference_format(of_b200, tmp_path):
     assert lines[3] == f"0 0 {fx[0, 0] / 128:.6f} {-fx[0, 0] / 128:.6f}"
     with pytest.raises(ValueError):
         of_b200.export_flow_txt(tmp_path / "no_such_dir" / "f.txt", u, v)
+
+
+def test_verifier_test_region_matches_the_mask_oracle(of_b200):
+    """of_b200.verifier_test_region gives the rectangle of get_test_region_mask
+    (python/optical_flow_verifier.py:96-138) for every pattern family."""
+    from oracle import flow_metrics_oracle as fm
+
+    for shape in ((240, 320), (1080, 1920), (101, 203)):
+        for name in ("translate_small", "translate_vertical", "rotate_small", "zoom_in", "translate_rotate", "no_motion"):
+            y0, y1, x0, x1 = of_b200.verifier_test_region(shape, name, 80)
+            mask = fm.test_region_mask(shape, name, 80)
+            want = np.zeros(shape, bool)
+            want[y0:y1, x0:x1] = True
+            assert np.array_equal(mask, want), (shape, name)
