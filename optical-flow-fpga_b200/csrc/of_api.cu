@@ -149,7 +149,7 @@ struct PyrPlan {
     std::vector<size_t> prev_off, curr_off;      // k >= 1
     std::vector<size_t> au_off, av_off, bu_off, bv_off;  // flow ping-pong (A of k = 0 is the caller's u, v)
     std::vector<size_t> warped_off;                      // warped current frame (split refinement)
-    size_t partial_off = 0, sel_off = 0, done_off = 0, total = 0;
+    size_t partial_off = 0, sel_off = 0, done_off = 0, cnt_off = 0, total = 0;
     int max_blocks = 0;
 };
 
@@ -193,6 +193,7 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
     p.partial_off = off; off += align_up((size_t)batch * p.max_blocks * 2 * sizeof(double));
     p.sel_off = off; off += align_up((size_t)levels * batch * sizeof(int));
     p.done_off = off; off += align_up((size_t)levels * batch * sizeof(int));
+    p.cnt_off = off; off += align_up((size_t)batch * sizeof(unsigned));  // ticket counters of the fused iteration tail
     p.total = off;
     return OF_OK;
 }
@@ -287,8 +288,24 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         ra.own_lo = 0;
         ra.own_hi = p.h[k];
         const bool fast_level = (mode == OF_MODE_FAST) && lk_refine_supported(ra, window);
+        // split refinement: the marching kernel's last warp per pair also does the convergence step
+        const bool fused_tail = fast_level && refine_split();
         for (int it = 0; it < iterations; ++it) {
             if (fast_level) {
+                if (fused_tail) {
+                    ra.tail.counter = reinterpret_cast<unsigned*>(ws + p.cnt_off);
+                    ra.tail.peers = 0;
+                    ra.tail.n_pixels = (double)p.h[k] * (double)p.w[k];
+                    ra.tail.sel = sel_k;
+                    ra.tail.done = done_k;
+                    ra.tail.iters_executed = iters_dev ? iters_dev + ref_level : nullptr;
+                    ra.tail.iters_pair_stride = levels;
+                    ra.tail.residuals = resid_dev ? resid_dev + (size_t)ref_level * iterations * 2 : nullptr;
+                    ra.tail.resid_pair_stride = (size_t)levels * iterations * 2;
+                    ra.tail.iteration = it;
+                    OF_CUDA(launch_lk_refine_split(ra, F(p.warped_off[k]), batch, &cnt.n, stream));
+                    continue;
+                }
                 if (refine_split())
                     OF_CUDA(launch_lk_refine_split(ra, F(p.warped_off[k]), batch, &cnt.n, stream));
                 else

@@ -25,6 +25,40 @@ struct SmemOptIn {
     }
 };
 
+// ---- tail of a refinement iteration, optionally fused into the marching kernel -----------
+constexpr int PEER_MAX_WORLD = 8;  // one NVSwitch domain
+constexpr int PEER_SLOTS = 64;     // flag / exchange slots, indexed by sequence number
+// what a kernel needs to signal / wait for the other ranks (peer.cu, peer_device.cuh)
+struct PeerSync {
+    char* peer[PEER_MAX_WORLD];  // arena base of every rank as mapped in this process
+    int world, rank;
+    size_t flag_off;  // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD] in every arena
+    size_t xchg_off;  // double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
+    // sequence number of this collective = *run_id * ops_per_run + op: the run counter lives in
+    // device memory (bumped by the first kernel of every run), so a captured CUDA graph of a run
+    // can be replayed and still produces fresh, growing sequence numbers
+    const unsigned long long* run_id;
+    unsigned long long ops_per_run, op;
+    int* err;
+    unsigned long long timeout_ns;
+};
+// Convergence bookkeeping of one iteration.  counter != nullptr asks the marching kernel to do it
+// itself: the last warp of a pair to finish (ticket counter) reduces the pair's partials in a fixed
+// order, all-reduces them over the ranks if `peers`, and applies the test -- no separate launch.
+struct IterTail {
+    unsigned* counter;  // [batch], zero between launches
+    int peers;          // 0: this GPU holds the whole level; 1: all-reduce through `sync`
+    PeerSync sync;
+    double n_pixels;
+    int* sel;
+    int* done;
+    int* iters_executed;  // nullable; pair b at iters_executed[b * iters_pair_stride]
+    int iters_pair_stride;
+    float* residuals;     // nullable; pair b, iteration i at residuals[b * resid_pair_stride + 2 * i]
+    size_t resid_pair_stride;
+    int iteration;
+};
+
 // ---- K1 fast: warp-marching fused single-scale LK (lk_march.cu) ------------------------
 struct MarchArgs {
     const float* prev;
@@ -48,6 +82,7 @@ struct MarchArgs {
     int16_t* u16;
     int16_t* v16;
     int fx_quirk;
+    IterTail tail;  // REFINE: tail.counter != nullptr fuses the iteration's convergence step into the kernel
 };
 bool lk_march_supported(int H, int W, int window);
 // force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
@@ -81,6 +116,7 @@ struct RefineArgs {
     int row_lo, row_hi, own_lo, own_hi;
     int n_strips, n_bands, band_rows;  // filled by the launcher
     long long n_units;
+    IterTail tail;  // split form only: counter != nullptr -> the marching kernel finishes the iteration itself
 };
 bool lk_refine_supported(const RefineArgs& a, int window);
 int lk_refine_units_per_pair(int batch, int rows, int W);
@@ -162,8 +198,6 @@ cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1
                                cudaStream_t stream);
 
 // ---- peer-memory collectives of the row-band mode (peer.cu) ----------------------------
-constexpr int PEER_MAX_WORLD = 8;  // one NVSwitch domain
-constexpr int PEER_SLOTS = 64;     // flag / exchange slots, indexed by sequence number
 struct PeerView {
     char* peer[PEER_MAX_WORLD];  // arena base of every rank as mapped in this process (peer[rank] = own)
     int world, rank;
@@ -174,6 +208,7 @@ struct PeerView {
     const unsigned long long* run_id;
     unsigned long long ops_per_run;
 };
+void fill_peer_sync(PeerSync& s, const PeerView& pv, unsigned long long op);
 // first kernel of a run: ++*run_id
 cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_t stream);
 // rows of a plane (current ping-pong buffer: sel[0] ^ sel_xor ? src1 : src0) -> byte offset dst_off

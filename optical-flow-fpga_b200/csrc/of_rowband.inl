@@ -28,7 +28,7 @@ struct RowbandCtx {
     // arena offsets (bytes)
     size_t flag_off = 0, xchg_off = 0, err_off = 0, run_off = 0, sel_off = 0, done_off = 0, itx_off = 0, resid_off = 0;
     std::vector<size_t> prev_off, curr_off, au_off, av_off, bu_off, bv_off, gu_off, gv_off;
-    size_t warped_off = 0, partial_off = 0, total = 0;
+    size_t warped_off = 0, partial_off = 0, cnt_off = 0, total = 0;
     char* base = nullptr;
     char* peer[PEER_MAX_WORLD];
     bool ipc_opened[PEER_MAX_WORLD];
@@ -129,6 +129,7 @@ int of_rowband_create(of_rowband_t** out, int rank, int world, int height, int w
     c->done_off = take(sizeof(int) * levels);
     c->itx_off = take(sizeof(int) * levels);
     c->resid_off = take(sizeof(float) * levels * (iterations > 0 ? iterations : 1) * 2);
+    c->cnt_off = take(sizeof(unsigned));  // ticket counter of the fused iteration tail (zero between launches)
     for (auto* v : {&c->prev_off, &c->curr_off, &c->au_off, &c->av_off, &c->bu_off, &c->bv_off, &c->gu_off, &c->gv_off})
         v->assign(levels, 0);
     int max_blocks = 1;
@@ -336,6 +337,22 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
             if (b > a) {
                 ra.row_lo = lo;
                 ra.row_hi = hi;
+                if (fast_level && refine_split()) {
+                    // the marching kernel's last warp reduces, all-reduces (split levels) and decides
+                    ra.tail.counter = reinterpret_cast<unsigned*>(c.base + c.cnt_off);
+                    ra.tail.peers = repl ? 0 : 1;
+                    if (!repl) fill_peer_sync(ra.tail.sync, pv, op++);
+                    ra.tail.n_pixels = (double)h * (double)w;
+                    ra.tail.sel = sel_k;
+                    ra.tail.done = done_k;
+                    ra.tail.iters_executed = itx + ref_level;
+                    ra.tail.iters_pair_stride = 0;
+                    ra.tail.residuals = resid + (size_t)ref_level * (iters > 0 ? iters : 1) * 2;
+                    ra.tail.resid_pair_stride = 0;
+                    ra.tail.iteration = it;
+                    OF_CUDA(launch_lk_refine_split(ra, F(c.warped_off), 1, &cnt.n, st));
+                    continue;
+                }
                 if (fast_level) {
                     if (refine_split())
                         OF_CUDA(launch_lk_refine_split(ra, F(c.warped_off), 1, &cnt.n, st));

@@ -20,45 +20,15 @@
 // has a time-out (a peer that died must not hang the GPU): it sets a sticky error word that makes
 // all later waits fall through; the host reads it after the run.
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "of_common.cuh"
 #include "of_kernels.h"
+#include "peer_device.cuh"
 
 namespace ofb {
 
 namespace {
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// wait until flags[slot][r] >= seq; false on time-out or when an earlier wait already failed
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, int* err,
-                                          unsigned long long timeout_ns) {
-    if (*reinterpret_cast<volatile int*>(err) != 0) return false;
-    const unsigned long long t0 = global_timer_ns();
-    unsigned spins = 0;
-    while (ld_acquire_sys(flag) < seq) {
-        if ((++spins & 63u) == 0) {
-            if (global_timer_ns() - t0 > timeout_ns) {
-                atomicExch(err, 1);
-                return false;
-            }
-            __nanosleep(200);
-        }
-    }
-    return true;
-}
 
 struct PushArgs {
     const float* src[2];  // ping-pong candidates (same plane offsets), current = sel ? src[1] : src[0]
@@ -92,21 +62,7 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushArgs a) {
     }
 }
 
-struct SyncArgs {
-    char* peer[PEER_MAX_WORLD];
-    int world, rank;
-    size_t flag_off;  // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD] in every arena
-    size_t xchg_off;  // double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
-    // sequence number of this collective = *run_id * ops_per_run + op: the run counter lives in
-    // device memory (bumped by the first kernel of every run), so a captured CUDA graph of a run
-    // can be replayed and still produces fresh, growing sequence numbers
-    const unsigned long long* run_id;
-    unsigned long long ops_per_run, op;
-    int* err;
-    unsigned long long timeout_ns;
-};
-
-__global__ void __launch_bounds__(32) peer_sync_kernel(const SyncArgs a) {
+__global__ void __launch_bounds__(32) peer_sync_kernel(const PeerSync a) {
     const int r = threadIdx.x;
     const unsigned long long seq = *a.run_id * a.ops_per_run + a.op;
     const int slot = (int)(seq % PEER_SLOTS);
@@ -119,25 +75,16 @@ __global__ void __launch_bounds__(32) peer_sync_kernel(const SyncArgs a) {
 }
 
 struct AllreduceArgs {
-    SyncArgs s;
+    IterTail t;             // sel / done / trace of the level (pair 0), t.sync = the collective
     const double* partial;  // this rank's per-block sums of |du|, |dv| (nullptr: the rank owns no rows)
     int blocks;
-    double n_pixels;
-    int* sel;
-    int* done;
-    int* iters_executed;
-    float* residuals;  // [max_iters][2]
-    int iteration;
 };
 
+// stand-alone form of the iteration tail (exact mode's tile kernel, ranks without rows); the fast
+// path's marching kernel runs the same code in its last warp (lk_march.cu)
 __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const AllreduceArgs a) {
     __shared__ double red[2][8];
-    __shared__ double tot[PEER_MAX_WORLD][2];
-    __shared__ int ok[PEER_MAX_WORLD];
-    if (a.done[0]) {
-        // the level has converged: the ranks agree on that, nothing is exchanged for this iteration
-        return;
-    }
+    if (a.t.done[0]) return;  // the level has converged: the ranks agree on that, nothing is exchanged
     double su = 0.0, sv = 0.0;
     if (a.partial != nullptr) {
         for (int i = threadIdx.x; i < a.blocks; i += 256) {
@@ -155,52 +102,17 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const Allred
         red[1][threadIdx.x >> 5] = sv;
     }
     __syncthreads();
-    const unsigned long long seq = *a.s.run_id * a.s.ops_per_run + a.s.op;
-    const int r = threadIdx.x, slot = (int)(seq % PEER_SLOTS);
-    if (r < a.s.world) {
+    if (threadIdx.x < 32) {
         su = 0.0;
         sv = 0.0;
         for (int w = 0; w < 8; ++w) {
             su += red[0][w];
             sv += red[1][w];
         }
-        // publish (su, sv) in peer r's slot of this rank, then the flag
-        double* x = reinterpret_cast<double*>(a.s.peer[r] + a.s.xchg_off) + ((size_t)slot * PEER_MAX_WORLD + a.s.rank) * 2;
-        x[0] = su;
-        x[1] = sv;
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned long long*>(a.s.peer[r] + a.s.flag_off) + slot * PEER_MAX_WORLD + a.s.rank,
-                       seq);
-        // collect rank r's contribution from the local arena
-        const bool got = wait_flag(reinterpret_cast<const unsigned long long*>(a.s.peer[a.s.rank] + a.s.flag_off) +
-                                       slot * PEER_MAX_WORLD + r,
-                                   seq, a.s.err, a.s.timeout_ns);
-        const double* y = reinterpret_cast<const double*>(a.s.peer[a.s.rank] + a.s.xchg_off) + ((size_t)slot * PEER_MAX_WORLD + r) * 2;
-        tot[r][0] = got ? *reinterpret_cast<const volatile double*>(y) : 0.0;
-        tot[r][1] = got ? *reinterpret_cast<const volatile double*>(y + 1) : 0.0;
-        ok[r] = got ? 1 : 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tu = 0.0, tv = 0.0;
-        bool all = true;
-        for (int q = 0; q < a.s.world; ++q) {  // rank order: the same sum on every rank
-            tu += tot[q][0];
-            tv += tot[q][1];
-            all = all && ok[q];
-        }
-        if (!all) {
-            a.done[0] = 1;  // a peer never answered: stop iterating (the error word is set)
-            return;
-        }
-        const float mu = (float)(tu / a.n_pixels), mv = (float)(tv / a.n_pixels);
-        a.sel[0] ^= 1;
-        if (a.iters_executed) a.iters_executed[0] += 1;
-        if (a.residuals) {
-            a.residuals[2 * a.iteration + 0] = mu;
-            a.residuals[2 * a.iteration + 1] = mv;
-        }
-        if (mu < OF_CONVERGENCE_EPS && mv < OF_CONVERGENCE_EPS) a.done[0] = 1;
+        double tu, tv;
+        bool ok;
+        warp_peer_allreduce(a.t.sync, su, sv, tu, tv, ok);
+        if (threadIdx.x == 0) apply_convergence(a.t, 0, tu, tv, ok);
     }
 }
 
@@ -208,7 +120,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const Allred
 
 __global__ void peer_bump_run_kernel(unsigned long long* run_id) { *run_id += 1; }
 
-static void fill_sync(SyncArgs& s, const PeerView& pv, unsigned long long op) {
+void fill_peer_sync(PeerSync& s, const PeerView& pv, unsigned long long op) {
     for (int r = 0; r < PEER_MAX_WORLD; ++r) s.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
     s.world = pv.world;
     s.rank = pv.rank;
@@ -251,8 +163,8 @@ cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_
 }
 
 cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long op, int* launches, cudaStream_t stream) {
-    SyncArgs s;
-    fill_sync(s, pv, op);
+    PeerSync s;
+    fill_peer_sync(s, pv, op);
     if (launches) *launches += 1;
     peer_sync_kernel<<<1, 32, 0, stream>>>(s);
     return cudaGetLastError();
@@ -262,15 +174,19 @@ cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long 
                                          double n_pixels, int* sel, int* done, int* iters_executed, float* residuals,
                                          int iteration, int* launches, cudaStream_t stream) {
     AllreduceArgs a;
-    fill_sync(a.s, pv, op);
+    memset(&a, 0, sizeof(a));
+    fill_peer_sync(a.t.sync, pv, op);
+    a.t.peers = 1;
+    a.t.n_pixels = n_pixels;
+    a.t.sel = sel;
+    a.t.done = done;
+    a.t.iters_executed = iters_executed;
+    a.t.iters_pair_stride = 0;
+    a.t.residuals = residuals;
+    a.t.resid_pair_stride = 0;
+    a.t.iteration = iteration;
     a.partial = partial;
     a.blocks = blocks;
-    a.n_pixels = n_pixels;
-    a.sel = sel;
-    a.done = done;
-    a.iters_executed = iters_executed;
-    a.residuals = residuals;
-    a.iteration = iteration;
     if (launches) *launches += 1;
     peer_allreduce_update_kernel<<<1, 256, 0, stream>>>(a);
     return cudaGetLastError();
