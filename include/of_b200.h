@@ -41,9 +41,10 @@ typedef enum of_status {
 /* Arithmetic mode of the float path.
  * OF_MODE_EXACT  the reference's operation order (NumPy pairwise window sums, SciPy's
  *                float64 filters): bit-identical to the Python reference on any input.
- * OF_MODE_FAST   separable window sums in registers (the throughput kernels); bit-identical
- *                to the reference on uint8-valued frames (all partial sums exactly
- *                representable), tolerance-level otherwise. */
+ * OF_MODE_FAST   separable window sums in registers (the throughput kernels); single scale:
+ *                bit-identical to the reference on uint8-valued frames (all partial sums exactly
+ *                representable), tolerance-level otherwise.  Pyramidal: additionally fused
+ *                multiply-adds in the float64 Gaussian (one float32 ulp on ~5 values in 10^9). */
 #define OF_MODE_EXACT 0
 #define OF_MODE_FAST 1
 
@@ -126,10 +127,12 @@ int of_lk_pyramidal_f32_dev(const float* prev, const float* curr, float* u, floa
  * A rank of a row-band job holds full-size frames / flow planes but computes only its rows.
  * All four calls only enqueue work on `stream`. */
 
-/* one coarser pyramid level for a batch (device version of of_pyramid_down_f32) */
+/* one coarser pyramid level for a batch (device version of of_pyramid_down_f32).  mode:
+ * OF_MODE_EXACT = SciPy's bits; OF_MODE_FAST = what the fast pyramidal drivers use (fused
+ * multiply-adds in the float64 filter: about 5 values in 10^9 differ by one float32 ulp). */
 int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height, int width,
                             int out_height, int out_width, const double* weights, int radius,
-                            int row_lo, int row_hi /* output rows to produce */, void* stream);
+                            int row_lo, int row_hi /* output rows to produce */, int mode, void* stream);
 
 /* upsample_flow for target rows [row_lo, row_hi) only */
 int of_upsample_flow_f32_dev(const float* coarse_u, const float* coarse_v, float* u, float* v,

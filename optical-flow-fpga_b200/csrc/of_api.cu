@@ -237,9 +237,9 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
     lc[0] = curr;
     for (int k = 1; k < levels; ++k) {
         OF_CUDA(launch_pyramid_down(lp[k - 1], F(p.prev_off[k]), batch, p.h[k - 1], p.w[k - 1], p.h[k], p.w[k], gw,
-                                    radius, 0, p.h[k], &cnt.n, stream));
+                                    radius, 0, p.h[k], &cnt.n, stream, mode == OF_MODE_FAST));
         OF_CUDA(launch_pyramid_down(lc[k - 1], F(p.curr_off[k]), batch, p.h[k - 1], p.w[k - 1], p.h[k], p.w[k], gw,
-                                    radius, 0, p.h[k], &cnt.n, stream));
+                                    radius, 0, p.h[k], &cnt.n, stream, mode == OF_MODE_FAST));
         lp[k] = F(p.prev_off[k]);
         lc[k] = F(p.curr_off[k]);
     }
@@ -652,7 +652,8 @@ int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v
 }
 
 int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height, int width, int out_height,
-                            int out_width, const double* weights, int radius, int row_lo, int row_hi, void* stream) {
+                            int out_width, const double* weights, int radius, int row_lo, int row_hi, int mode,
+                            void* stream) {
     OF_TRY(check_frame(src, dst, height, width));
     if (out_height < 1 || out_width < 1) return fail(OF_ERR_INVALID_ARGUMENT, "output size must be >= 1");
     if (!weights || radius < 0 || radius > OF_MAX_GAUSS_RADIUS)
@@ -661,8 +662,9 @@ int of_pyramid_down_f32_dev(const float* src, float* dst, int batch, int height,
     OF_TRY(need_device());
     Counter cnt;
     if (row_lo < 0 || row_hi > out_height || row_lo >= row_hi) return fail(OF_ERR_INVALID_ARGUMENT, "bad output row range");
+    if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
     OF_CUDA(launch_pyramid_down(src, dst, batch, height, width, out_height, out_width, weights, radius, row_lo, row_hi,
-                                &cnt.n, static_cast<cudaStream_t>(stream)));
+                                &cnt.n, static_cast<cudaStream_t>(stream), mode == OF_MODE_FAST));
     return OF_OK;
 }
 

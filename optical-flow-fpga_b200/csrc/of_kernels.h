@@ -179,13 +179,15 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
                              int W, int* launches, cudaStream_t stream);
 // fused Gaussian (separable, float64 accumulate, float32 store per axis, reflect) + bilinear
 // resample on the np.linspace grid (lucas_kanade_pyramidal.py:44-59)
+// fast = true (fast mode of the pyramidal drivers only): fused multiply-adds in the float64 filter
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
                                 const double* weights, int radius, int row_lo, int row_hi, int* launches,
-                                cudaStream_t stream);
+                                cudaStream_t stream, bool fast = false);
 // the same level by the marching kernel (pyramid_march.cu): radius 8, decimation step in [1, 6]
 bool pyramid_march_supported(int H, int W, int oh, int ow, int radius);
 cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
-                                 const double* weights, int row_lo, int row_hi, int* launches, cudaStream_t stream);
+                                 const double* weights, int row_lo, int row_hi, bool fused_multiply_add, int* launches,
+                                 cudaStream_t stream);
 cudaError_t launch_warp(const float* img, const float* fu, const float* fv, float* out, int batch, int H, int W,
                         int* launches, cudaStream_t stream);
 // coarse flow (selected ping-pong buffer) -> fine grid, scaled (lucas_kanade_pyramidal.py:100-138)

@@ -268,9 +268,9 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         lc[k] = F(c.curr_off[k]);
         if (b > a) {
             OF_CUDA(launch_pyramid_down(lp[k - 1], F(c.prev_off[k]), 1, c.h[k - 1], c.w[k - 1], c.h[k], c.w[k], c.gw, c.radius,
-                                        a, b, &cnt.n, st));
+                                        a, b, &cnt.n, st, c.mode == OF_MODE_FAST));
             OF_CUDA(launch_pyramid_down(lc[k - 1], F(c.curr_off[k]), 1, c.h[k - 1], c.w[k - 1], c.h[k], c.w[k], c.gw, c.radius,
-                                        a, b, &cnt.n, st));
+                                        a, b, &cnt.n, st, c.mode == OF_MODE_FAST));
         }
         if (world > 1 && !replicated(k)) {
             const size_t first = (size_t)a * c.w[k], count = (size_t)(b - a) * c.w[k];

@@ -219,7 +219,7 @@ static int pyr_tile_extent(int limit, double step) {
 
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
                                 const double* weights, int radius, int row_lo, int row_hi, int* launches,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, bool fast) {
     if (radius < 0 || radius > PYR_MAX_RADIUS || oh < 1 || ow < 1 || batch > 65535) return cudaErrorInvalidValue;
     if (row_lo < 0 || row_hi > oh || row_lo >= row_hi) return cudaErrorInvalidValue;
     // sigma = 2 (the reference's pyramid) on a ~2x decimation: the marching kernel; anything else
@@ -230,7 +230,7 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
         return e != nullptr && strcmp(e, "tile") == 0;
     }();
     if (!force_tile && pyramid_march_supported(H, W, oh, ow, radius))
-        return launch_pyramid_march(src, dst, batch, H, W, oh, ow, weights, row_lo, row_hi, launches, stream);
+        return launch_pyramid_march(src, dst, batch, H, W, oh, ow, weights, row_lo, row_hi, fast, launches, stream);
     PyrArgs a;
     a.src = src;
     a.dst = dst;

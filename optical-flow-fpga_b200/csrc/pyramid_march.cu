@@ -61,13 +61,25 @@ __device__ __forceinline__ int pm_reflect(int i, int n) {
 }
 
 // centre tap, then the symmetric pairs from the outside in (scipy's correlate1d for symmetric kernels)
+// FMA = false: products and sums rounded separately, like the C code SciPy compiles to on x86-64 (exact
+// mode, and the stand-alone of_pyramid_down entry points).  FMA = true (fast mode of the pyramidal
+// drivers): each pair term is one fused multiply-add -- 17 instead of 25 float64 operations.  The float64
+// sums then differ in their last bits, which survives the float32 store only when the sum sits within
+// ~2^-52 of a float32 rounding boundary: about 5 values in 10^9 move by one float32 ulp.
+template <bool FMA>
 __device__ __forceinline__ double pm_gauss(const double* x, const double* w) {
     double acc = dmul(x[PM_R], w[PM_R]);
 #pragma unroll
-    for (int ii = -PM_R; ii < 0; ++ii) acc = dadd(acc, dmul(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R]));
+    for (int ii = -PM_R; ii < 0; ++ii) {
+        if (FMA)
+            acc = fma(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R], acc);
+        else
+            acc = dadd(acc, dmul(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R]));
+    }
     return acc;
 }
 
+template <bool FMA>
 __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrMarchArgs a) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
     // axis-0 results of two consecutive steps, already rounded to float32 but kept as float64 so
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrM
             }
             double* tw = tmp + (it & 1) * (PM_CH * PM_TPITCH) + tid;
 #pragma unroll
-            for (int k = 0; k < PM_CH; ++k) tw[k * PM_TPITCH] = (double)(float)pm_gauss(x + k, a.w);
+            for (int k = 0; k < PM_CH; ++k) tw[k * PM_TPITCH] = (double)(float)pm_gauss<FMA>(x + k, a.w);
 #pragma unroll
             for (int k = 0; k < 2 * PM_R; ++k) x[k] = x[k + PM_CH];
         }
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrM
             }
             float o[PM_SEG];
 #pragma unroll
-            for (int k = 0; k < PM_SEG; ++k) o[k] = (float)pm_gauss(t + k, a.w);
+            for (int k = 0; k < PM_SEG; ++k) o[k] = (float)pm_gauss<FMA>(t + k, a.w);
             float4* out4 = reinterpret_cast<float4*>(smo + ((hs * PM_CH + hk) & (PM_RING - 1)) * PM_SPITCH + hseg * PM_SEG);
             out4[0] = make_float4(o[0], o[1], o[2], o[3]);
             out4[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -200,7 +212,8 @@ bool pyramid_march_supported(int H, int W, int oh, int ow, int radius) {
 }
 
 cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
-                                 const double* weights, int row_lo, int row_hi, int* launches, cudaStream_t stream) {
+                                 const double* weights, int row_lo, int row_hi, bool fused_multiply_add, int* launches,
+                                 cudaStream_t stream) {
     if (batch > 65535 || row_lo < 0 || row_hi > oh || row_lo >= row_hi) return cudaErrorInvalidValue;
     PyrMarchArgs a;
     a.src = src;
@@ -239,14 +252,18 @@ cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H,
         }
     }
     const int n_bands = (rows + a.band_rows - 1) / a.band_rows;
-    static SmemOptIn opt_in;
+    static SmemOptIn opt_in[2];
     {
-        cudaError_t e = opt_in.ensure(pyramid_march_kernel, PM_SMEM_BYTES);
+        cudaError_t e = fused_multiply_add ? opt_in[1].ensure(pyramid_march_kernel<true>, PM_SMEM_BYTES)
+                                           : opt_in[0].ensure(pyramid_march_kernel<false>, PM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
     }
     if (launches) *launches += 1;
     dim3 grid(n_strips, n_bands, batch);
-    pyramid_march_kernel<<<grid, PM_THREADS, PM_SMEM_BYTES, stream>>>(a);
+    if (fused_multiply_add)
+        pyramid_march_kernel<true><<<grid, PM_THREADS, PM_SMEM_BYTES, stream>>>(a);
+    else
+        pyramid_march_kernel<false><<<grid, PM_THREADS, PM_SMEM_BYTES, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -264,7 +264,7 @@ class CudaBackend:
         h, w = img.shape
         out = self.empty(int(h * 0.5), int(w * 0.5))
         self.ofb.pyramid_down_dev(img.data_ptr(), out.data_ptr(), 1, h, w, out.shape[0], out.shape[1], self._stream(),
-                                  2.0, lo, out.shape[0] if hi is None else hi)
+                                  2.0, lo, out.shape[0] if hi is None else hi, getattr(self, "mode", 0))
         return out
 
     # ---- device-side iteration control (no host round trip inside a level) ----------------
@@ -343,6 +343,7 @@ def lk_pyramidal_rowbands(
 
         mode = of_b200.default_mode()
     rank, world = comm.rank, comm.world
+    backend.mode = mode  # the fast drivers' pyramid uses the fast filter (same bits as the single-GPU fast path)
     halo = window_size // 2 + 1
     if halo > GROW - 1:
         raise ValueError("row-band mode supports window_size <= 5")

@@ -71,7 +71,7 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, C.c_size_t, _vp, _vp, _vp],
     ),
     "of_lk_single_scale_fx_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "of_pyramid_down_f32_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "of_pyramid_down_f32_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "of_lk_refine_pingpong_f32_dev": (
         _i,
         [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp],
@@ -378,12 +378,12 @@ def lk_pyramidal_dev(
 
 
 def pyramid_down_dev(src_ptr, dst_ptr, batch, height, width, out_height, out_width, stream=0, sigma: float = 2.0,
-                     row_lo: int = 0, row_hi: Optional[int] = None):
+                     row_lo: int = 0, row_hi: Optional[int] = None, mode: int = MODE_EXACT):
     wts = gaussian_weights(sigma)
     _check(
         lib().of_pyramid_down_f32_dev(
             src_ptr, dst_ptr, batch, height, width, out_height, out_width, _ptr(wts), (len(wts) - 1) // 2,
-            row_lo, out_height if row_hi is None else row_hi, stream,
+            row_lo, out_height if row_hi is None else row_hi, int(mode), stream,
         )
     )
 
