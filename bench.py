@@ -401,12 +401,23 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             # native driver: one C call per pair enqueues everything; the ranks meet through peer
             # memory inside the kernels.  The whole step is captured in a CUDA graph (the sequence
             # numbers of the collectives come from a device-side run counter, so replays are valid).
-            plan = ofd.PeerRowbands(H, W, wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST)
+            # Frame pairs of a step are independent: up to OF_B200_ROWBAND_LANES (default 2) of them are
+            # in flight at once, each on its own stream with its own arena, so the launch-latency-bound
+            # kernels of the coarse levels of one pair overlap with the other pair's.
+            n_lanes = max(1, min(B, int(os.environ.get("OF_B200_ROWBAND_LANES", "2"))))
+            plans = [ofd.PeerRowbands(H, W, wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST) for _ in range(n_lanes)]
+            plan = plans[0]
+            lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
 
             def enqueue():
-                st = torch.cuda.current_stream().cuda_stream
+                main = torch.cuda.current_stream()
+                for s_ in lanes:  # fork
+                    s_.wait_stream(main)
                 for b in range(B):
-                    plan.ctx.run(prev[b].data_ptr(), curr[b].data_ptr(), u[b].data_ptr(), v[b].data_ptr(), st)
+                    k = b % n_lanes
+                    plans[k].ctx.run(prev[b].data_ptr(), curr[b].data_ptr(), u[b].data_ptr(), v[b].data_ptr(), lanes[k].cuda_stream)
+                for s_ in lanes:  # join
+                    main.wait_stream(s_)
 
             enqueue()  # first call: function attributes, driver entry points
             torch.cuda.synchronize()
@@ -452,7 +463,9 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     sampler.stop()
     launches = of_b200.kernel_launches() - launches0
     if rowband and os.environ.get("OF_B200_ROWBAND", "peer") != "nccl":
-        plan.trace()  # raises if a wait on a peer timed out
+        torch.cuda.synchronize()
+        for pl in plans:
+            pl.trace()  # raises if a wait on a peer timed out
         if os.environ.get("OF_B200_GRAPH", "1") == "1":
             # graph replays do not pass through the library's launch counter: count one step's launches
             l0 = of_b200.kernel_launches()
@@ -508,6 +521,17 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
                   "frac_pixels_diff_gt_1e-3": frac_big, "mean_abs_diff_px": mean_diff}
         if wl["pyramidal"] and H * W > 3840 * 2160:
             parity["checked_against"] = "exact-mode GPU path (bit-identical to the oracle in tests/)"
+        if rowband:
+            # the row-band result of the step's last pair against the single-GPU fast driver: same bits
+            ws1 = torch.empty(of_b200.lk_pyramidal_workspace_bytes(1, H, W, wl["levels"], wl["iters"]), dtype=torch.uint8, device=dev)
+            u1, v1 = torch.empty_like(prev[0]), torch.empty_like(prev[0])
+            of_b200.lk_pyramidal_dev(prev[B - 1].data_ptr(), curr[B - 1].data_ptr(), u1.data_ptr(), v1.data_ptr(), 1, H, W,
+                                     wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST, ws1.data_ptr(), ws1.numel(), None,
+                                     None, stream)
+            torch.cuda.synchronize()
+            parity["rowband_bit_equal_to_single_gpu"] = bool(torch.equal(u1.view(torch.int32), u[B - 1].view(torch.int32)) and
+                                                             torch.equal(v1.view(torch.int32), v[B - 1].view(torch.int32)))
+            del ws1, u1, v1
         if wl["pyramidal"]:
             parity["note"] = ("fast mode: warp is the reference's float64 bilinear bit for bit, window sums are "
                               "separable float32 (different association), so ill-conditioned pixels can move")
