@@ -1,4 +1,8 @@
-N=${1:-8}
+#!/bin/bash
+# Multi-GPU runs on one box:  gpurun --gpus N --timeout 900 -- 'bash tools/gpu/scale.sh N'
+#   batch sharding (default workload, pyramidal 4K), row bands over NVLink peer memory (8K), and the
+#   bit-equality check of the row-band result against the single-GPU driver (fast and exact mode)
+N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
 set -x
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
