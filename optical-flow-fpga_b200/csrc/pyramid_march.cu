@@ -68,22 +68,14 @@ __device__ __forceinline__ int pm_reflect(int i, int n) {
 // ~2^-52 of a float32 rounding boundary: about 5 values in 10^9 move by one float32 ulp.
 template <bool FMA>
 __device__ __forceinline__ double pm_gauss(const double* x, const double* w) {
-    if (FMA) {
-        // two independent accumulation chains (outer / inner pairs alternate): half the dependent depth
-        double a0 = dmul(x[PM_R], w[PM_R]), a1 = dmul(dadd(x[0], x[2 * PM_R]), w[0]);
-#pragma unroll
-        for (int ii = -PM_R + 1; ii < 0; ++ii) {
-            const double pair = dadd(x[PM_R + ii], x[PM_R - ii]);
-            if ((ii + PM_R) & 1)
-                a0 = fma(pair, w[ii + PM_R], a0);
-            else
-                a1 = fma(pair, w[ii + PM_R], a1);
-        }
-        return dadd(a0, a1);
-    }
     double acc = dmul(x[PM_R], w[PM_R]);
 #pragma unroll
-    for (int ii = -PM_R; ii < 0; ++ii) acc = dadd(acc, dmul(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R]));
+    for (int ii = -PM_R; ii < 0; ++ii) {
+        if (FMA)
+            acc = fma(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R], acc);
+        else
+            acc = dadd(acc, dmul(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R]));
+    }
     return acc;
 }
 
