@@ -405,19 +405,10 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             # in flight at once, each on its own stream with its own arena, so the launch-latency-bound
             # kernels of the coarse levels of one pair overlap with the other pair's.
             n_lanes = max(1, min(B, int(os.environ.get("OF_B200_ROWBAND_LANES", "2"))))
-            plans = [ofd.PeerRowbands(H, W, wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST) for _ in range(n_lanes)]
-            plan = plans[0]
-            lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)]
+            lanes = ofd.PeerRowbandLanes(H, W, wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST, lanes=n_lanes)
 
             def enqueue():
-                main = torch.cuda.current_stream()
-                for s_ in lanes:  # fork
-                    s_.wait_stream(main)
-                for b in range(B):
-                    k = b % n_lanes
-                    plans[k].ctx.run(prev[b].data_ptr(), curr[b].data_ptr(), u[b].data_ptr(), v[b].data_ptr(), lanes[k].cuda_stream)
-                for s_ in lanes:  # join
-                    main.wait_stream(s_)
+                lanes.run_batch(prev, curr, u, v)
 
             enqueue()  # first call: function attributes, driver entry points
             torch.cuda.synchronize()
@@ -463,9 +454,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     sampler.stop()
     launches = of_b200.kernel_launches() - launches0
     if rowband and os.environ.get("OF_B200_ROWBAND", "peer") != "nccl":
-        torch.cuda.synchronize()
-        for pl in plans:
-            pl.trace()  # raises if a wait on a peer timed out
+        lanes.trace()  # waits for the device; raises if a wait on a peer timed out
         if os.environ.get("OF_B200_GRAPH", "1") == "1":
             # graph replays do not pass through the library's launch counter: count one step's launches
             l0 = of_b200.kernel_launches()

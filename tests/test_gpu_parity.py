@@ -582,6 +582,42 @@ def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iter
             cx.close()
 
 
+def test_peer_rowband_lanes_single_process(ofb):
+    """distributed.PeerRowbandLanes without a process group (one rank): three pairs over two lanes,
+    plain and replayed from a CUDA graph; every pair equals the single-GPU driver bit for bit."""
+    import torch
+
+    import distributed as ofd
+    import synthetic
+
+    H, W = 200, 248
+    prev, curr, _ = synthetic.make_pairs_numpy(3, H, W, seed=17)
+    curr = np.stack([np.roll(c, 2, axis=0) for c in curr])
+    want = [ofb.lk_pyramidal(prev[b], curr[b], 3, 5, 3, mode=ofb.MODE_FAST) for b in range(3)]
+    dev = torch.device("cuda", 0)
+    pd, cd = torch.from_numpy(prev).to(dev), torch.from_numpy(curr).to(dev)
+    u, v = torch.zeros_like(pd), torch.zeros_like(pd)
+    lanes = ofd.PeerRowbandLanes(H, W, 3, 5, 3, ofb.MODE_FAST, lanes=2)
+    try:
+        lanes.run_batch(pd, cd, u, v)
+        lanes.trace()
+        for b in range(3):
+            assert_bit_equal(u[b].cpu().numpy(), want[b][0], f"pair {b} u")
+            assert_bit_equal(v[b].cpu().numpy(), want[b][1], f"pair {b} v")
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            lanes.run_batch(pd, cd, u, v)
+        for _ in range(2):
+            u.zero_()
+            v.zero_()
+            graph.replay()
+            lanes.trace()
+            for b in range(3):
+                assert_bit_equal(u[b].cpu().numpy(), want[b][0], f"graph replay, pair {b} u")
+    finally:
+        lanes.close()
+
+
 def test_native_rowband_driver_times_out_instead_of_hanging(ofb):
     """A rank whose peer never shows up must not wedge the GPU: every spin has a time-out that sets a
     sticky error word, the run drains, and of_rowband_trace reports it."""
