@@ -206,3 +206,35 @@ def test_verifier_test_region_matches_the_mask_oracle(of_b200):
             want = np.zeros(shape, bool)
             want[y0:y1, x0:x1] = True
             assert np.array_equal(mask, want), (shape, name)
+
+
+def test_header_is_plain_c_and_a_c_program_links(of_b200, tmp_path):
+    """include/of_b200.h is C99 (no C++ or torch types in the signatures) and a plain C caller links
+    against libof_b200.so; without a GPU the compute call fails loudly with OF_ERR_NO_DEVICE."""
+    import shutil
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    hdr = ROOT / "include" / "of_b200.h"
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", str(hdr)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "of_b200.h"\n'
+        "int main(void) {\n"
+        "    float z[49] = {0}, u[49], v[49];\n"
+        "    int rc = of_lk_single_scale_f32(z, z, u, v, 1, 7, 7, 5, OF_MODE_EXACT);\n"
+        '    printf("%d %d %d\\n", of_version(), of_device_count(), rc);\n'
+        "    return 0;\n}\n"
+    )
+    exe = tmp_path / "caller"
+    lib_dir = str(of_b200.LIB_PATH.parent)
+    res = subprocess.run([gcc, "-std=c99", f"-I{ROOT / 'include'}", str(src), "-o", str(exe), f"-L{lib_dir}", "-lof_b200",
+                          f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()
+    version, devices, rc = (int(x) for x in out)
+    assert version == 100
+    assert rc == (0 if devices > 0 else 4)  # OF_OK with a GPU, OF_ERR_NO_DEVICE without: never a CPU result
