@@ -232,6 +232,9 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
     if (!c.peers_set) return fail(OF_ERR_INVALID_ARGUMENT, "peer arenas have not been connected");
     OF_TRY(check_frame(prev, curr, c.H, c.W));
     if ((u == nullptr) != (v == nullptr)) return fail(OF_ERR_INVALID_ARGUMENT, "pass both u and v or neither");
+    int dev_now = -1;
+    OF_CUDA(cudaGetDevice(&dev_now));
+    if (dev_now != c.device) return fail(OF_ERR_INVALID_ARGUMENT, "of_rowband_run must be called with the context's device current");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Counter cnt;
     const PeerView pv = rb_view(c);
