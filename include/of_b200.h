@@ -205,6 +205,16 @@ int of_apply_motion_u8(const uint8_t* frames, uint8_t* out, int batch, int heigh
 int of_apply_motion_u8_dev(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* dx,
                            const double* dy, double cval, void* stream);
 
+/* apply_motion_opencv(frame, params) of python/generate_test_suite.py:165-204, i.e.
+ * cv2.warpAffine(frame, M, (W, H), flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, borderValue=cval) on uint8
+ * frames, bit-identical to OpenCV's fixed-point bilinear warp (10-bit coordinates, 1/32-pixel weights,
+ * 15-bit coefficients).  matrices: [batch][6] forward 2x3 matrices, row-major, HOST memory in both
+ * flavours (they are inverted on the host in OpenCV's operation order and travel as kernel arguments). */
+int of_warp_affine_u8(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* matrices,
+                      int cval);
+int of_warp_affine_u8_dev(const uint8_t* frames, uint8_t* out, int batch, int height, int width,
+                          const double* matrices, int cval, void* stream);
+
 /* ---- flow-field error metrics on the device ----------------------------------------------
  * compute_all_metrics(u_pred, v_pred, u_true, v_true, mask) of python/flow_metrics.py:166-201 for a
  * batch of flow fields, the mask being the verifier's rectangular test region

@@ -1031,6 +1031,60 @@ int of_apply_motion_u8(const uint8_t* frames, uint8_t* out, int batch, int heigh
     return OF_OK;
 }
 
+// warpAffine's inversion of the forward 2x3 matrix (imgwarp.cpp, !WARP_INVERSE_MAP), same operation
+// order; volatile keeps the host compiler from contracting a*b+c into an FMA
+static void invert_affine_cv(const double* m, double* out) {
+    volatile double D = m[0] * m[4];
+    volatile double t = m[1] * m[3];
+    D = D - t;
+    D = D != 0 ? 1.0 / D : 0.0;
+    volatile double a11 = m[4] * D, a22 = m[0] * D;
+    volatile double m1 = m[1] * (-D), m3 = m[3] * (-D);
+    volatile double p0 = -a11 * m[2], p1 = m1 * m[5];
+    volatile double q0 = -m3 * m[2], q1 = a22 * m[5];
+    out[0] = a11;
+    out[1] = m1;
+    out[2] = p0 - p1;
+    out[3] = m3;
+    out[4] = a22;
+    out[5] = q0 - q1;
+}
+
+int of_warp_affine_u8_dev(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* matrices,
+                          int cval, void* stream) {
+    OF_TRY(check_frame(frames, out, height, width));
+    if (!matrices) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (frames == out) return fail(OF_ERR_INVALID_ARGUMENT, "in-place warping is not supported");
+    if (batch < 1 || batch > 65535 || height > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch and height must be in 1..65535");
+    if (cval < 0 || cval > 255) return fail(OF_ERR_INVALID_ARGUMENT, "border value must be in 0..255");
+    OF_TRY(need_device());
+    std::vector<double> minv((size_t)batch * 6);
+    for (int b = 0; b < batch; ++b) invert_affine_cv(matrices + (size_t)b * 6, minv.data() + (size_t)b * 6);
+    Counter cnt;
+    OF_CUDA(launch_warp_affine(frames, out, minv.data(), batch, height, width, cval, &cnt.n, static_cast<cudaStream_t>(stream)));
+    return OF_OK;
+}
+
+int of_warp_affine_u8(const uint8_t* frames, uint8_t* out, int batch, int height, int width, const double* matrices,
+                      int cval) {
+    OF_TRY(check_frame(frames, out, height, width));
+    if (!matrices) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
+    if (batch < 1 || batch > 65535 || height > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch and height must be in 1..65535");
+    OF_TRY(need_device());
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    OF_TRY(host_streams());
+    const size_t n = (size_t)batch * height * width;
+    uint8_t *ds, *dd;
+    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&ds)));
+    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dd)));
+    cudaStream_t st = g_streams[0];
+    OF_CUDA(cudaMemcpyAsync(ds, frames, n, cudaMemcpyHostToDevice, st));
+    OF_TRY(of_warp_affine_u8_dev(ds, dd, batch, height, width, matrices, cval, st));
+    OF_CUDA(cudaMemcpyAsync(out, dd, n, cudaMemcpyDeviceToHost, st));
+    OF_CUDA(cudaStreamSynchronize(st));
+    return OF_OK;
+}
+
 size_t of_flow_metrics_workspace_bytes(int batch, int height, int width) {
     if (batch < 1 || height < 1 || width < 1) return 0;
     return align_up((size_t)batch * metrics_blocks_per_pair(height, width) * 6 * sizeof(double));

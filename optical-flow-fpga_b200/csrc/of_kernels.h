@@ -236,6 +236,10 @@ cudaError_t launch_flow_metrics(const float* u, const float* v, const float* u_t
 cudaError_t launch_apply_motion(const uint8_t* src, uint8_t* dst, const double* dx, const double* dy, int batch, int H,
                                 int W, double cval, int* launches, cudaStream_t stream);
 
+// cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT) in OpenCV's fixed point; minv: [batch][6] inverted matrices (host)
+cudaError_t launch_warp_affine(const uint8_t* src, uint8_t* dst, const double* minv, int batch, int H, int W, int cval,
+                               int* launches, cudaStream_t stream);
+
 // ---- fixed-point mode (lk_fixed.cu) ----------------------------------------------------
 cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,
                             int mirror_avg_quirk, int* launches, cudaStream_t stream);

@@ -90,6 +90,8 @@ SIGNATURES = {
     "of_export_flow_fx_txt": (_i, [C.c_char_p, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "of_apply_motion_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, C.c_double]),
     "of_apply_motion_u8_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, C.c_double, _vp]),
+    "of_warp_affine_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i]),
+    "of_warp_affine_u8_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "of_flow_metrics_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "of_flow_metrics_f32_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "of_flow_metrics_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -504,6 +506,36 @@ def apply_motion_u8_batch(frames_u8, dx, dy, cval: float = 128.0) -> np.ndarray:
 
 def apply_motion_u8_dev(frames_ptr, out_ptr, batch, height, width, dx_ptr, dy_ptr, cval: float = 128.0, stream=0):
     _check(lib().of_apply_motion_u8_dev(frames_ptr, out_ptr, batch, height, width, dx_ptr, dy_ptr, float(cval), stream))
+
+
+def motion_matrix(width: int, height: int, dx: float = 0.0, dy: float = 0.0, rotation: float = 0.0, scale: float = 1.0):
+    """The 2x3 matrix apply_motion_opencv builds (generate_test_suite.py:183-190): cv2.getRotationMatrix2D
+    about the frame centre (libm cos / sin of angle * (pi / 180)), then the translation."""
+    import math
+
+    a = rotation * (math.pi / 180.0)
+    alpha, beta = math.cos(a) * scale, math.sin(a) * scale
+    cx, cy = width / 2.0, height / 2.0
+    return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy + dx], [-beta, alpha, beta * cx + (1 - alpha) * cy + dy]],
+                    np.float64)
+
+
+def warp_affine_u8_batch(frames_u8, matrices, cval: int = 128) -> np.ndarray:
+    """cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT, cval) for [B, H, W] (or [H, W]) uint8 frames with one
+    2x3 forward matrix per frame; bit-identical to OpenCV (apply_motion_opencv of generate_test_suite.py)."""
+    f = np.ascontiguousarray(frames_u8)
+    if f.dtype != np.uint8:
+        raise ValueError("frames must be uint8")
+    single = f.ndim == 2
+    if single:
+        f = f[None]
+    if f.ndim != 3:
+        raise ValueError("frames must be [B, H, W] or [H, W]")
+    b, h, w = f.shape
+    m = np.ascontiguousarray(np.broadcast_to(np.asarray(matrices, dtype=np.float64).reshape(-1, 2, 3), (b, 2, 3)))
+    out = np.empty_like(f)
+    _check(lib().of_warp_affine_u8(_ptr(f), _ptr(out), b, h, w, _ptr(m), int(cval)))
+    return out[0] if single else out
 
 
 METRIC_NAMES = ("mae_u", "mae_v", "rmse", "epe", "aae")

@@ -498,6 +498,34 @@ def test_apply_motion_kernel_equals_scipy_shift(ofb):
     assert_bit_equal(ofb.apply_motion_u8_batch(frames[0], 1.5, 0.0, cval=7.0), po.apply_motion(frames[0], 1.5, 0.0, 7.0), "cval")
 
 
+def test_warp_affine_kernel_equals_opencv(ofb):
+    """of_warp_affine_u8 against the reference's apply_motion_opencv outputs (cv2.warpAffine; the 13 verifier
+    parameter sets + 7 random affine maps on two frames, tests/golden/motion.npz) and against the oracle on
+    a larger frame; the matrices come from of_b200.motion_matrix (= cv2.getRotationMatrix2D + translation)."""
+    from conftest import GOLDEN
+    from oracle import pattern_oracle as po
+
+    z = np.load(GOLDEN / "motion.npz")
+    cases = z["affine_cases"]
+    for name, src in (("texture", z["texture_128x96"]), ("noise", z["noise_53x37"])):
+        h, w = src.shape
+        mats = np.stack([ofb.motion_matrix(w, h, *c) for c in cases])
+        for i, c in enumerate(cases):
+            assert np.array_equal(mats[i], po.motion_matrix(w, h, *c))
+        got = ofb.warp_affine_u8_batch(np.repeat(src[None], len(cases), axis=0), mats)
+        for i in range(len(cases)):
+            assert_bit_equal(got[i], z[f"{name}_affine_{i}"], f"{name} affine {cases[i].tolist()}")
+    rng = np.random.default_rng(21)
+    frames = rng.integers(0, 256, (60, 270, 481)).astype(np.uint8)  # more pairs than one launch carries matrices for
+    params = np.stack([rng.uniform(-9, 9, 60), rng.uniform(-9, 9, 60), rng.uniform(-25, 25, 60), rng.uniform(0.7, 1.4, 60)], axis=1)
+    mats = np.stack([ofb.motion_matrix(481, 270, *p) for p in params])
+    got = ofb.warp_affine_u8_batch(frames, mats)
+    for b in (0, 1, 47, 48, 59):
+        assert_bit_equal(got[b], po.warp_affine_u8(frames[b], mats[b]), f"random affine {b}")
+    ident = ofb.warp_affine_u8_batch(frames[0], ofb.motion_matrix(481, 270))
+    assert_bit_equal(ident, frames[0], "identity")
+
+
 def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_frames):
     """of_flow_metrics_f32 (compute_all_metrics over the verifier's test region, on the device):
     all 13 patterns in ONE batched call per method.  Against the reference's

@@ -138,3 +138,7 @@ def test_pattern_oracle_equals_reference_generators():
     for i, (dx, dy) in enumerate(z["cases"]):
         for name, src in (("texture", z["texture_128x96"]), ("noise", z["noise_53x37"])):
             assert np.array_equal(po.apply_motion(src, dx, dy), z[f"{name}_shift_{i}"]), (name, dx, dy)
+    for i, (dx, dy, rot, sc) in enumerate(z["affine_cases"]):  # apply_motion_opencv = cv2.warpAffine in fixed point
+        for name, src in (("texture", z["texture_128x96"]), ("noise", z["noise_53x37"])):
+            assert np.array_equal(po.apply_motion_opencv(src, dx, dy, rot, sc), z[f"{name}_affine_{i}"]), (name, i)
+
