@@ -526,6 +526,42 @@ def test_warp_affine_kernel_equals_opencv(ofb):
     assert_bit_equal(ident, frames[0], "identity")
 
 
+# motion parameters of the reference's 13 verifier patterns (python/generate_test_suite.py:59-136): dx, dy, rotation, scale
+VERIFIER_PATTERNS = {
+    "translate_small": (0.5, 0.5, 0.0, 1.0), "translate_medium": (2.0, 0.0, 0.0, 1.0), "translate_large": (15.0, 0.0, 0.0, 1.0),
+    "translate_vertical": (0.0, 10.0, 0.0, 1.0), "translate_diagonal": (10.0, 10.0, 0.0, 1.0), "rotate_small": (0.0, 0.0, 2.0, 1.0),
+    "rotate_medium": (0.0, 0.0, 5.0, 1.0), "rotate_large": (0.0, 0.0, 15.0, 1.0), "zoom_in": (0.0, 0.0, 0.0, 1.1),
+    "zoom_out": (0.0, 0.0, 0.0, 0.9), "translate_rotate": (5.0, 5.0, 3.0, 1.0), "no_motion": (0.0, 0.0, 0.0, 1.0),
+    "translate_extreme": (30.0, 20.0, 0.0, 1.0),
+}
+
+
+def test_verifier_pipeline_on_the_device_reproduces_the_baseline(ofb, golden_index, golden_frames):
+    """The reference's whole acceptance loop with every step on the GPU backend: second frames by
+    of_warp_affine_u8 from the base texture (must equal the reference generator's frame_01 bit for bit),
+    single-scale LK on the uint8 frames, metrics by of_flow_metrics_f32 -- against
+    python/verification_baseline.json."""
+    names = list(golden_index["patterns"])
+    assert sorted(names) == sorted(VERIFIER_PATTERNS)
+    base = golden_frames[names[0]][0]
+    for n in names:
+        assert np.array_equal(golden_frames[n][0], base)  # every pattern starts from the same texture
+    h, w = base.shape
+    mats = np.stack([ofb.motion_matrix(w, h, *VERIFIER_PATTERNS[n]) for n in names])
+    second = ofb.warp_affine_u8_batch(np.repeat(base[None], len(names), axis=0), mats)
+    for i, n in enumerate(names):
+        assert_bit_equal(second[i], golden_frames[n][1], f"generated frame_01 of {n}")
+    u, v = ofb.lk_single_scale_u8_batch(np.repeat(base[None], len(names), axis=0), second, 5, ofb.MODE_FAST)
+    crop = golden_index["center_crop"]
+    for i, n in enumerate(names):
+        entry = golden_index["patterns"][n]
+        assert sha(u[i]) == entry["single_scale"]["sha256_u"] and sha(v[i]) == entry["single_scale"]["sha256_v"], n
+        m = ofb.flow_metrics_batch(u[i], v[i], entry["ground_truth"]["u"], entry["ground_truth"]["v"],
+                                   ofb.verifier_test_region((h, w), n, crop))[0]
+        for k, val in entry["verification_baseline"]["single_scale"].items():
+            assert m[k] == pytest.approx(val, rel=2e-6, abs=1e-6), (n, k)
+
+
 def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_frames):
     """of_flow_metrics_f32 (compute_all_metrics over the verifier's test region, on the device):
     all 13 patterns in ONE batched call per method.  Against the reference's
