@@ -238,3 +238,12 @@ def test_header_is_plain_c_and_a_c_program_links(of_b200, tmp_path):
     version, devices, rc = (int(x) for x in out)
     assert version == 100
     assert rc == (0 if devices > 0 else 4)  # OF_OK with a GPU, OF_ERR_NO_DEVICE without: never a CPU result
+
+
+def test_motion_matrix_matches_the_pattern_oracle(of_b200):
+    """of_b200.motion_matrix (cv2.getRotationMatrix2D + translation, generate_test_suite.py:183-190) equals the
+    oracle's restatement, which tests/golden/make_golden_motion.py checked against cv2 itself."""
+    from oracle import pattern_oracle as po
+
+    for args in ((320, 240, 0.5, 0.5, 0.0, 1.0), (320, 240, 0.0, 0.0, 15.0, 1.0), (131, 97, -3.25, 7.5, -11.0, 1.17)):
+        assert np.array_equal(of_b200.motion_matrix(*args), po.motion_matrix(*args))
