@@ -39,6 +39,8 @@ WORKLOADS = {
     # name: (batch per GPU, H, W, pyramidal?, levels, iterations)
     "single_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1),
     "pyramidal_4k": dict(batch=16, H=2160, W=3840, pyramidal=True, levels=3, iters=3),
+    # the same path in exact mode (the reference's operation order: bit-identical on any input)
+    "pyramidal_4k_exact": dict(batch=4, H=2160, W=3840, pyramidal=True, levels=3, iters=3, variant="exact"),
     # secondary modes of the single-scale path (device-resident only)
     "single_1080p_exact": dict(batch=64, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="exact"),
     "fixed_1080p": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1, variant="fixed"),
@@ -379,7 +381,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
 
         def step():
             of_b200.lk_single_scale_u8_dev(p8.data_ptr(), c8.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, WINDOW, stream)
-    elif variant == "exact":
+    elif variant == "exact" and not wl["pyramidal"]:
         def step():
             of_b200.lk_single_scale_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
                                         WINDOW, of_b200.MODE_EXACT, stream)
@@ -423,9 +425,11 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
         ws_bytes = of_b200.lk_pyramidal_workspace_bytes(B, H, W, wl["levels"], wl["iters"])
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 
+        pyr_mode = of_b200.MODE_EXACT if variant == "exact" else of_b200.MODE_FAST
+
         def step():
             of_b200.lk_pyramidal_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
-                                     wl["levels"], WINDOW, wl["iters"], of_b200.MODE_FAST, ws.data_ptr(), ws_bytes,
+                                     wl["levels"], WINDOW, wl["iters"], pyr_mode, ws.data_ptr(), ws_bytes,
                                      None, None, stream)
     else:
         def step():
