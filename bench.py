@@ -525,7 +525,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             parity["rowband_bit_equal_to_single_gpu"] = bool(torch.equal(u1.view(torch.int32), u[B - 1].view(torch.int32)) and
                                                              torch.equal(v1.view(torch.int32), v[B - 1].view(torch.int32)))
             del ws1, u1, v1
-        if wl["pyramidal"]:
+        if wl["pyramidal"] and variant != "exact":
             parity["note"] = ("fast mode: warp is the reference's float64 bilinear bit for bit, window sums are "
                               "separable float32 (different association), so ill-conditioned pixels can move")
 
