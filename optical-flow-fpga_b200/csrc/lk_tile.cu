@@ -66,8 +66,37 @@ __device__ __forceinline__ float numpy_order_sum(const float* __restrict__ a, co
     return fadd(0.0f, res);
 }
 
+// np.sum's order as a streaming accumulator: taps arrive in index order t = 0 .. N-1 (N = WIN * WIN >= 8),
+// t is a compile-time constant after unrolling.  Lets one thread feed the same per-pixel product
+// into the windows of two adjacent output pixels.
+template <int WIN>
+struct NpAcc {
+    float lane[8];
+    float res;
+};
+__device__ __forceinline__ float np_tree(const float* lane) {
+    return fadd(fadd(fadd(lane[0], lane[1]), fadd(lane[2], lane[3])), fadd(fadd(lane[4], lane[5]), fadd(lane[6], lane[7])));
+}
+template <int WIN>
+__device__ __forceinline__ void np_add(NpAcc<WIN>& s, int t, float p) {
+    constexpr int N = WIN * WIN, FULL = N - (N % 8);
+    if (t < 8) {
+        s.lane[t] = p;
+    } else if (t < FULL) {
+        s.lane[t & 7] = fadd(s.lane[t & 7], p);
+    } else {
+        if (t == FULL) s.res = np_tree(s.lane);
+        s.res = fadd(s.res, p);
+    }
+}
+template <int WIN>
+__device__ __forceinline__ float np_finish(const NpAcc<WIN>& s) {
+    constexpr int N = WIN * WIN, FULL = N - (N % 8);
+    return fadd(0.0f, FULL == N ? np_tree(s.lane) : s.res);
+}
+
 template <int SRC, int WIN>
-__global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
+__global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel(TileArgs a) {
     extern __shared__ float smem[];
     constexpr int HW = WIN / 2;
     constexpr int GW = TX + 2 * HW, GH = TY + 2 * HW;  // gradient tile
@@ -154,24 +183,14 @@ __global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
     }
     __syncthreads();
 
-    // stage C: window sums in NumPy's order + Cramer
+    // stage C: window sums in NumPy's order + Cramer.  One thread = two horizontally adjacent output
+    // pixels: every gradient pixel of the 5 x 6 neighbourhood is loaded once and its five products are
+    // formed once, then fed into both windows' accumulators (same tap order per window as np.sum).
     double acc_u = 0.0, acc_v = 0.0;
-    for (int o = tid; o < TY * TX; o += TILE_THREADS) {
-        const int r = o / TX, c = o % TX;
-        const int y = oy + r, x = ox + c;
-        if (y >= y_end || x >= W) continue;
+    auto emit = [&](int y, int x, float sxx, float syy, float sxy, float sxt, float syt) {
+        if (y >= y_end || x >= W) return;
         float u = 0.0f, v = 0.0f;
-        if (y >= HW && y < H - HW && x >= HW && x < W - HW) {
-            const float* wx = gx + r * GW + c;
-            const float* wy = gy + r * GW + c;
-            const float* wt = gt + r * GW + c;
-            const float sxx = numpy_order_sum<WIN>(wx, wx, GW);
-            const float syy = numpy_order_sum<WIN>(wy, wy, GW);
-            const float sxy = numpy_order_sum<WIN>(wx, wy, GW);
-            const float sxt = numpy_order_sum<WIN>(wx, wt, GW);
-            const float syt = numpy_order_sum<WIN>(wy, wt, GW);
-            cramer_solve(sxx, syy, sxy, sxt, syt, u, v);
-        }
+        if (y >= HW && y < H - HW && x >= HW && x < W - HW) cramer_solve(sxx, syy, sxy, sxt, syt, u, v);
         const size_t go = (size_t)y * W + x;
         if (SRC == SRC_WARP) {
             fout_u[go] = fadd(__ldg(fin_u + go), u);  // flow += d
@@ -183,6 +202,41 @@ __global__ void __launch_bounds__(TILE_THREADS) lk_tile_kernel(TileArgs a) {
         } else {
             a.out_u[pair * plane + go] = u;
             a.out_v[pair * plane + go] = v;
+        }
+    };
+    if (WIN * WIN >= 8) {
+        for (int item = tid; item < TY * (TX / 2); item += TILE_THREADS) {
+            const int r = item / (TX / 2), c = 2 * (item % (TX / 2));
+            const int y = oy + r, x = ox + c;
+            if (y >= y_end || x >= W) continue;
+            NpAcc<WIN> s0[5], s1[5];
+#pragma unroll
+            for (int i = 0; i < WIN; ++i) {
+                const float* rx = gx + (r + i) * GW + c;
+                const float* ry = gy + (r + i) * GW + c;
+                const float* rt = gt + (r + i) * GW + c;
+#pragma unroll
+                for (int k = 0; k <= WIN; ++k) {
+                    const float vx = rx[k], vy = ry[k], vt = rt[k];
+                    const float p[5] = {fmul(vx, vx), fmul(vy, vy), fmul(vx, vy), fmul(vx, vt), fmul(vy, vt)};
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        if (k < WIN) np_add<WIN>(s0[q], WIN * i + k, p[q]);
+                        if (k >= 1) np_add<WIN>(s1[q], WIN * i + k - 1, p[q]);
+                    }
+                }
+            }
+            emit(y, x, np_finish<WIN>(s0[0]), np_finish<WIN>(s0[1]), np_finish<WIN>(s0[2]), np_finish<WIN>(s0[3]), np_finish<WIN>(s0[4]));
+            emit(y, x + 1, np_finish<WIN>(s1[0]), np_finish<WIN>(s1[1]), np_finish<WIN>(s1[2]), np_finish<WIN>(s1[3]), np_finish<WIN>(s1[4]));
+        }
+    } else {
+        for (int o = tid; o < TY * TX; o += TILE_THREADS) {
+            const int r = o / TX, c = o % TX;
+            const float* wx = gx + r * GW + c;
+            const float* wy = gy + r * GW + c;
+            const float* wt = gt + r * GW + c;
+            emit(oy + r, ox + c, numpy_order_sum<WIN>(wx, wx, GW), numpy_order_sum<WIN>(wy, wy, GW),
+                 numpy_order_sum<WIN>(wx, wy, GW), numpy_order_sum<WIN>(wx, wt, GW), numpy_order_sum<WIN>(wy, wt, GW));
         }
     }
 
