@@ -215,9 +215,21 @@ __global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel
                 const float* rx = gx + (r + i) * GW + c;
                 const float* ry = gy + (r + i) * GW + c;
                 const float* rt = gt + (r + i) * GW + c;
+                // WIN + 1 values per plane as 64-bit loads (c is even, the pitch GW is even): consecutive
+                // lanes read consecutive 8-byte words, no bank conflicts
+                float ax[WIN + 1], ay[WIN + 1], at[WIN + 1];
+#pragma unroll
+                for (int k = 0; k <= WIN; k += 2) {
+                    const float2 fx2 = *reinterpret_cast<const float2*>(rx + k);
+                    const float2 fy2 = *reinterpret_cast<const float2*>(ry + k);
+                    const float2 ft2 = *reinterpret_cast<const float2*>(rt + k);
+                    ax[k] = fx2.x; ax[k + 1] = fx2.y;
+                    ay[k] = fy2.x; ay[k + 1] = fy2.y;
+                    at[k] = ft2.x; at[k + 1] = ft2.y;
+                }
 #pragma unroll
                 for (int k = 0; k <= WIN; ++k) {
-                    const float vx = rx[k], vy = ry[k], vt = rt[k];
+                    const float vx = ax[k], vy = ay[k], vt = at[k];
                     const float p[5] = {fmul(vx, vx), fmul(vy, vy), fmul(vx, vy), fmul(vx, vt), fmul(vy, vt)};
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
