@@ -7,6 +7,8 @@
 //               (python/lucas_kanade_pyramidal.py:203-214): warp_image (float64 bilinear,
 //               outside -> 0) -> single-scale LK against the previous frame -> flow += d,
 //               plus per-block partial sums of |du|, |dv| for the convergence test.
+//   SRC_WARPED  the same iteration with the warped frame already in HBM (written by
+//               warp_rows_kernel<double>, lk_march.cu): stage A is SRC_FRAMES' on (prev, warped).
 //
 // Order of operations that is mirrored (pinned by tests/golden):
 //   * avg = (p + c) / 2;  Sobel = true 2-D convolution, symmetric border, float32
@@ -96,8 +98,10 @@ __device__ __forceinline__ float np_finish(const NpAcc<WIN>& s) {
 }
 
 template <int SRC, int WIN>
-__global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel(TileArgs a) {
+__global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? (SRC == SRC_WARPED ? 3 : 2) : 1) lk_tile_kernel(TileArgs a) {
     extern __shared__ float smem[];
+    constexpr bool FLOW = (SRC == SRC_WARP || SRC == SRC_WARPED);  // refinement iteration: flow_out = flow_in + d
+    constexpr bool GATHER = (SRC == SRC_WARP);                     // stage A gathers the current frame itself
     constexpr int HW = WIN / 2;
     constexpr int GW = TX + 2 * HW, GH = TY + 2 * HW;  // gradient tile
     constexpr int FW = GW + 2, FH = GH + 2;            // frame tile (Sobel halo)
@@ -108,24 +112,32 @@ __global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel
     float* fc = fp + FH * FW;  // curr (or warped curr), then It
 
     const int pair = blockIdx.z;
-    if (SRC == SRC_WARP && a.done != nullptr && a.done[pair]) return;  // level already converged
+    if (FLOW && a.done != nullptr && a.done[pair]) return;  // level already converged
 
     const int H = a.H, W = a.W;
     const size_t plane = (size_t)H * W;
-    const int ox = blockIdx.x * TX, oy = (SRC == SRC_WARP ? a.row_lo : 0) + blockIdx.y * TY;
-    const int y_end = (SRC == SRC_WARP) ? a.row_hi : H;
+    const int ox = blockIdx.x * TX, oy = (FLOW ? a.row_lo : 0) + blockIdx.y * TY;
+    const int y_end = FLOW ? a.row_hi : H;
     const int tid = threadIdx.x;
 
     const float* fin_u = nullptr;
     const float* fin_v = nullptr;
     float* fout_u = nullptr;
     float* fout_v = nullptr;
-    if (SRC == SRC_WARP) {
+    if (FLOW) {
         const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
-        fin_u = a.flow_u[cur] + pair * plane;
-        fin_v = a.flow_v[cur] + pair * plane;
-        fout_u = a.flow_u[cur ^ 1] + pair * plane;
-        fout_v = a.flow_v[cur ^ 1] + pair * plane;
+        if (SRC == SRC_WARPED) {
+            // selects instead of a run-time index into the parameter block (which costs a local copy)
+            fin_u = (cur ? a.flow_u[1] : a.flow_u[0]) + pair * plane;
+            fin_v = (cur ? a.flow_v[1] : a.flow_v[0]) + pair * plane;
+            fout_u = (cur ? a.flow_u[0] : a.flow_u[1]) + pair * plane;
+            fout_v = (cur ? a.flow_v[0] : a.flow_v[1]) + pair * plane;
+        } else {
+            fin_u = a.flow_u[cur] + pair * plane;
+            fin_v = a.flow_v[cur] + pair * plane;
+            fout_u = a.flow_u[cur ^ 1] + pair * plane;
+            fout_v = a.flow_v[cur ^ 1] + pair * plane;
+        }
     }
 
     if (SRC == SRC_GRADS) {
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel
             const size_t o = (size_t)y * W + x;
             const float p = __ldg(prev + o);
             float c;
-            if (SRC == SRC_WARP) {
+            if (GATHER) {
                 // warp_image: coordinates are int64 + float32 -> float64
                 const double yw = dadd((double)y, (double)__ldg(fin_v + o));
                 const double xw = dadd((double)x, (double)__ldg(fin_u + o));
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel
         float u = 0.0f, v = 0.0f;
         if (y >= HW && y < H - HW && x >= HW && x < W - HW) cramer_solve(sxx, syy, sxy, sxt, syt, u, v);
         const size_t go = (size_t)y * W + x;
-        if (SRC == SRC_WARP) {
+        if (FLOW) {
             fout_u[go] = fadd(__ldg(fin_u + go), u);  // flow += d
             fout_v[go] = fadd(__ldg(fin_v + go), v);
             if (y >= a.own_lo && y < a.own_hi) {
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? 2 : 1) lk_tile_kernel
         }
     }
 
-    if (SRC == SRC_WARP && a.partial != nullptr) {
+    if (FLOW && a.partial != nullptr) {
         // deterministic block reduction (fixed shuffle tree, then warps in order)
         __shared__ double red[2][TILE_THREADS / 32];
 #pragma unroll
@@ -394,7 +406,7 @@ static cudaError_t launch_one(const TileArgs& a, int batch, cudaStream_t stream)
     constexpr int GW = TX + 2 * HW, GH = TY + 2 * HW;
     constexpr int FW = GW + 2, FH = GH + 2;
     const size_t smem = (size_t)(3 * GH * GW + 2 * FH * FW) * sizeof(float);
-    const int rows = (SRC == SRC_WARP) ? a.row_hi - a.row_lo : a.H;
+    const int rows = (SRC == SRC_WARP || SRC == SRC_WARPED) ? a.row_hi - a.row_lo : a.H;
     if (rows <= 0) return cudaErrorInvalidValue;
     dim3 grid((a.W + TX - 1) / TX, (rows + TY - 1) / TY, batch);
     lk_tile_kernel<SRC, WIN><<<grid, TILE_THREADS, smem, stream>>>(a);
@@ -420,6 +432,7 @@ cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, in
     switch (src) {
         case SRC_FRAMES: return launch_src<SRC_FRAMES>(window, a, batch, stream);
         case SRC_WARP: return launch_src<SRC_WARP>(window, a, batch, stream);
+        case SRC_WARPED: return launch_src<SRC_WARPED>(window, a, batch, stream);
         case SRC_GRADS: return launch_src<SRC_GRADS>(window, a, batch, stream);
         default: return cudaErrorInvalidValue;
     }

@@ -209,6 +209,21 @@ bool refine_split() {
     return v == 1;
 }
 
+#ifndef OF_EXACT_REFINE_SPLIT_DEFAULT
+#define OF_EXACT_REFINE_SPLIT_DEFAULT 0  // flipped to 1 once the split form has passed the GPU suite
+#endif
+// exact-mode refinement: "split" = warp kernel with float64 fractions + the tile kernel on (prev, warped)
+// ; "fused" = the tile kernel gathers its halo tile itself (the first implementation: 1.5 gathers per
+// pixel at 16 warps per SM, latency-bound).  Same bits; OF_B200_EXACT_REFINE=split|fused picks.
+bool exact_refine_split() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OF_B200_EXACT_REFINE");
+        v = e ? (std::string(e) == "split" ? 1 : 0) : OF_EXACT_REFINE_SPLIT_DEFAULT;
+    }
+    return v == 1;
+}
+
 int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int levels,
                   int window, int iterations, int mode, const double* gw, int radius, void* workspace, size_t ws_bytes,
                   int* iters_dev, float* resid_dev, cudaStream_t stream, Counter& cnt) {
@@ -329,7 +344,15 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                 a.row_hi = p.h[k];
                 a.own_lo = 0;
                 a.own_hi = p.h[k];
-                OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
+                if (exact_refine_split()) {
+                    // the whole level warped once (coalesced gathers, 4 samples per thread), then the tile
+                    // kernel reads it like a frame: its replicated border is the warp at the clamped pixel
+                    OF_CUDA(launch_warp_rows(ra, F(p.warped_off[k]), 0, p.h[k], true, batch, &cnt.n, stream));
+                    a.in1 = F(p.warped_off[k]);
+                    OF_CUDA(launch_lk_tile(SRC_WARPED, window, a, batch, &cnt.n, stream));
+                } else {
+                    OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
+                }
             }
             IterFinalizeArgs f;
             f.partial = partial;

@@ -124,22 +124,28 @@ cudaError_t launch_lk_refine(const RefineArgs& a, int batch, int* launches, cuda
 // Split form of the same iteration: warp_rows (gather the current frame through the flow into
 // `warped`, rows [row_lo - 3, row_hi + 3)) followed by the K1 marching kernel in REFINE mode.
 cudaError_t launch_lk_refine_split(const RefineArgs& a, float* warped, int batch, int* launches, cudaStream_t stream);
+// The warp alone: warped[pair][y][x] = bilinear(curr, y + v, x + u) for rows [row_lo, row_hi) of every pair
+// that has not converged, flow = the current ping-pong buffer of `a`.  exact = float64 sample fractions
+// (warp_image's bits for any flow); false = the float32 fractions of the fast path.
+cudaError_t launch_warp_rows(const RefineArgs& a, float* warped, int row_lo, int row_hi, bool exact, int batch,
+                             int* launches, cudaStream_t stream);
 
 // ---- K1/K3 exact: tile kernel in the reference's operation order (lk_tile.cu) ----------
-enum TileSource { SRC_FRAMES = 0, SRC_WARP = 1, SRC_GRADS = 2 };
+enum TileSource { SRC_FRAMES = 0, SRC_WARP = 1, SRC_GRADS = 2, SRC_WARPED = 3 };
 struct TileArgs {
     // SRC_FRAMES: in0 = prev, in1 = curr.  SRC_WARP: in0 = prev level, in1 = curr level (gathered
-    // through the flow).  SRC_GRADS: in0 = Ix, in1 = Iy, in2 = It.
+    // through the flow).  SRC_GRADS: in0 = Ix, in1 = Iy, in2 = It.  SRC_WARPED: SRC_WARP with
+    // in1 = the current level already warped through the current flow (launch_warp_rows, exact).
     const float* in0;
     const float* in1;
     const float* in2;
-    // SRC_WARP only: ping-pong flow buffers; sel[pair] says which one is current (0 = A).
+    // SRC_WARP / SRC_WARPED: ping-pong flow buffers; sel[pair] says which one is current (0 = A).
     float* flow_u[2];
     float* flow_v[2];
     const int* sel;    // nullable: A is the input, B the output
     int sel_xor;       // current buffer = sel[pair] ^ sel_xor
     const int* done;   // nullable: pairs whose level has converged are skipped
-    double* partial;   // [pair][blocks_per_pair][2] sums of |du|, |dv| (SRC_WARP)
+    double* partial;   // [pair][blocks_per_pair][2] sums of |du|, |dv| (SRC_WARP / SRC_WARPED)
     // SRC_FRAMES / SRC_GRADS outputs
     float* out_u;
     float* out_v;

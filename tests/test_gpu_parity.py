@@ -279,6 +279,34 @@ def test_pyramidal_other_presets_against_oracle(ofb, levels, iters, shape):
     assert_bit_equal(v, vo, "v")
 
 
+def test_exact_refinement_split_equals_fused(ofb):
+    """Exact mode, the two forms of a refinement iteration: warp_rows_kernel<double> + tile kernel on
+    (prev, warped) [default] and the tile kernel that gathers its own halo [OF_B200_EXACT_REFINE=fused]
+    give the same bits.  The switch is read once per process, so the fused form runs in a child.
+    Flow of both signs and large enough to leave the frame (warp's outside -> 0 rule), ragged width."""
+    import os
+    import subprocess
+
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        f"sys.path.insert(0, {str(BACKEND_DIR)!r})\n"
+        "import of_b200\n"
+        "from scipy.ndimage import gaussian_filter, shift\n"
+        "rng = np.random.default_rng(77)\n"
+        "p = gaussian_filter((rng.random((2, 150, 203)) * 255).astype(np.float32), (0, 1.5, 1.5))\n"
+        "c = np.stack([shift(p[0], (-2.6, 3.4), order=1, mode='nearest'), shift(p[1], (1.2, -0.3), order=1, mode='nearest')]).astype(np.float32)\n"
+        "u, v = of_b200.lk_pyramidal_batch(p, c, 3, 5, 4, mode=of_b200.MODE_EXACT)\n"
+        "print(hashlib.sha256(u.tobytes() + v.tobytes()).hexdigest())\n"
+    )
+    got = {}
+    for form in ("split", "fused"):
+        env = dict(os.environ, OF_B200_EXACT_REFINE=form)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr[-2000:]
+        got[form] = res.stdout.strip().splitlines()[-1]
+    assert got["split"] == got["fused"]
+
+
 # ---------------------------------------------------------------------------------------
 # full-size frames: oracle on one pair + size-independent properties
 # ---------------------------------------------------------------------------------------
