@@ -526,8 +526,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
                                                              torch.equal(v1.view(torch.int32), v[B - 1].view(torch.int32)))
             del ws1, u1, v1
         if wl["pyramidal"] and variant != "exact":
-            parity["note"] = ("fast mode: warp is the reference's float64 bilinear bit for bit, window sums are "
-                              "separable float32 (different association), so ill-conditioned pixels can move")
+            parity["note"] = ("fast mode: the warp blends in float64 like the reference but with float32 sample fractions, "
+                              "window sums are separable float32 (different association), so ill-conditioned pixels can move")
 
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
     e2e = None

@@ -22,6 +22,9 @@
 // stage C does the window sums + solve; Ix/Iy/It never go to HBM.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "of_common.cuh"
 #include "of_kernels.h"
 
@@ -426,9 +429,25 @@ static cudaError_t launch_src(int window, const TileArgs& a, int batch, cudaStre
     }
 }
 
+#ifndef OF_TILE_V2_DEFAULT
+#define OF_TILE_V2_DEFAULT 0  // flipped to 1 once lk_tile5_kernel has passed the GPU suite
+#endif
+// window 5 on frames (single scale, or prev + warped plane): the second version of the kernel (lk_tile5.cu)
+// unless OF_B200_TILE=v1.  Same bits; every other window / source takes the kernel above.
+static bool tile_v2() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OF_B200_TILE");
+        v = e ? (strcmp(e, "v2") == 0 ? 1 : 0) : OF_TILE_V2_DEFAULT;
+    }
+    return v == 1;
+}
+
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream) {
     if (batch > 65535) return cudaErrorInvalidValue;
     if (launches) *launches += 1;
+    if (window == 5 && (src == SRC_FRAMES || src == SRC_WARPED) && (size_t)a.H * a.W < ((size_t)1 << 31) && tile_v2())
+        return launch_lk_tile5(src, a, batch, stream);
     switch (src) {
         case SRC_FRAMES: return launch_src<SRC_FRAMES>(window, a, batch, stream);
         case SRC_WARP: return launch_src<SRC_WARP>(window, a, batch, stream);

@@ -153,6 +153,8 @@ struct TileArgs {
     int row_lo, row_hi, own_lo, own_hi;  // SRC_WARP row-band mode (see RefineArgs); else 0, H, 0, H
 };
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream);
+// window 5, SRC_FRAMES / SRC_WARPED: second version of the kernel (lk_tile5.cu); called through launch_lk_tile
+cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t stream);
 int lk_tile_blocks_per_pair(int rows, int W);
 bool lk_tile_window_supported(int window);
 

@@ -92,7 +92,8 @@ def test_pyramidal_13_patterns_bit_exact_and_metrics(ofb, golden_index, golden_f
 
 
 def test_pyramidal_fast_mode_13_patterns_within_tolerance(ofb, golden_index, golden_frames):
-    """FAST pyramidal (register-marching refinement kernel): the warp is exact, the window sums
+    """FAST pyramidal (register-marching refinement kernel): the warp blends in float64 with float32
+    sample fractions (one rounding away from the reference's for negative flow), the window sums
     are separable float32.  Contract: MAE / EPE equal to the reference's to 3 decimals on every
     verifier pattern; per-pixel deviations are confined to ill-conditioned pixels."""
     report = {}
@@ -279,11 +280,12 @@ def test_pyramidal_other_presets_against_oracle(ofb, levels, iters, shape):
     assert_bit_equal(v, vo, "v")
 
 
-def test_exact_refinement_split_equals_fused(ofb):
-    """Exact mode, the two forms of a refinement iteration: warp_rows_kernel<double> + tile kernel on
-    (prev, warped) [default] and the tile kernel that gathers its own halo [OF_B200_EXACT_REFINE=fused]
-    give the same bits.  The switch is read once per process, so the fused form runs in a child.
-    Flow of both signs and large enough to leave the frame (warp's outside -> 0 rule), ragged width."""
+def test_exact_mode_kernel_variants_give_the_same_bits(ofb):
+    """Exact mode has two switches, each read once per process, so every combination runs in a child:
+    OF_B200_EXACT_REFINE = split (warp_rows_kernel<double> + tile kernel on (prev, warped)) | fused (the tile
+    kernel gathers its own halo), OF_B200_TILE = v1 (lk_tile_kernel) | v2 (lk_tile5_kernel, window 5).
+    Single-scale on float frames (ragged shapes, one narrower than a tile) and a 3-level pyramidal run whose
+    flow has both signs and leaves the frame (warp's outside -> 0 rule) must hash identically."""
     import os
     import subprocess
 
@@ -293,18 +295,25 @@ def test_exact_refinement_split_equals_fused(ofb):
         "import of_b200\n"
         "from scipy.ndimage import gaussian_filter, shift\n"
         "rng = np.random.default_rng(77)\n"
+        "h = hashlib.sha256()\n"
+        "for shape in ((150, 203), (37, 61), (16, 64), (5, 5), (129, 260)):\n"
+        "    a = (rng.standard_normal(shape) * 50).astype(np.float32)\n"
+        "    b = (a + rng.standard_normal(shape) * 3).astype(np.float32)\n"
+        "    u, v = of_b200.lk_single_scale(a, b, 5, mode=of_b200.MODE_EXACT)\n"
+        "    h.update(u.tobytes() + v.tobytes())\n"
         "p = gaussian_filter((rng.random((2, 150, 203)) * 255).astype(np.float32), (0, 1.5, 1.5))\n"
         "c = np.stack([shift(p[0], (-2.6, 3.4), order=1, mode='nearest'), shift(p[1], (1.2, -0.3), order=1, mode='nearest')]).astype(np.float32)\n"
         "u, v = of_b200.lk_pyramidal_batch(p, c, 3, 5, 4, mode=of_b200.MODE_EXACT)\n"
-        "print(hashlib.sha256(u.tobytes() + v.tobytes()).hexdigest())\n"
+        "h.update(u.tobytes() + v.tobytes())\n"
+        "print(h.hexdigest())\n"
     )
     got = {}
-    for form in ("split", "fused"):
-        env = dict(os.environ, OF_B200_EXACT_REFINE=form)
+    for refine, tile in (("fused", "v1"), ("split", "v1"), ("split", "v2")):
+        env = dict(os.environ, OF_B200_EXACT_REFINE=refine, OF_B200_TILE=tile)
         res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
         assert res.returncode == 0, res.stderr[-2000:]
-        got[form] = res.stdout.strip().splitlines()[-1]
-    assert got["split"] == got["fused"]
+        got[(refine, tile)] = res.stdout.strip().splitlines()[-1]
+    assert len(set(got.values())) == 1, got
 
 
 # ---------------------------------------------------------------------------------------
