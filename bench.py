@@ -591,7 +591,7 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             "peak_source": peak_src,
             "algorithmic_bytes_per_pixel": bpp,
             "kernel": ("whole pyramidal step (all launches)" if wl["pyramidal"] else
-                       {"fixed": "lk_fixed_kernel", "exact": "lk_tile_kernel<SRC_FRAMES, 5>", "u8": "lk_march_kernel<true, false, true> (uint8 frames)"}.get(variant, "lk_march_kernel<true, false> (one launch per step)")),
+                       {"fixed": "lk_fixed_kernel", "exact": "lk_tile5_kernel<SRC_FRAMES>", "u8": "lk_march_kernel<true, false, true> (uint8 frames)"}.get(variant, "lk_march_kernel<true, false> (one launch per step)")),
             "kernel_ms": kernel_ms,
             "frac_of_nominal_8TBs": achieved / 8000.0,
         },

@@ -430,7 +430,7 @@ static cudaError_t launch_src(int window, const TileArgs& a, int batch, cudaStre
 }
 
 #ifndef OF_TILE_V2_DEFAULT
-#define OF_TILE_V2_DEFAULT 0  // flipped to 1 once lk_tile5_kernel has passed the GPU suite
+#define OF_TILE_V2_DEFAULT 1  // lk_tile5_kernel passed the GPU suite (profiles/r01c_pytest_gpu_exact_v2.log)
 #endif
 // window 5 on frames (single scale, or prev + warped plane): the second version of the kernel (lk_tile5.cu)
 // unless OF_B200_TILE=v1.  Same bits; every other window / source takes the kernel above.

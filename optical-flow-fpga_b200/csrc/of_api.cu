@@ -210,7 +210,7 @@ bool refine_split() {
 }
 
 #ifndef OF_EXACT_REFINE_SPLIT_DEFAULT
-#define OF_EXACT_REFINE_SPLIT_DEFAULT 0  // flipped to 1 once the split form has passed the GPU suite
+#define OF_EXACT_REFINE_SPLIT_DEFAULT 1  // split passed the GPU suite (profiles/r01c_pytest_gpu_exact_v2.log)
 #endif
 // exact-mode refinement: "split" = warp kernel with float64 fractions + the tile kernel on (prev, warped)
 // ; "fused" = the tile kernel gathers its halo tile itself (the first implementation: 1.5 gathers per
