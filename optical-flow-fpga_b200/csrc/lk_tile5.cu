@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(T5_THREADS, 3) lk_tile5_kernel(TileArgs a) {
 
 }  // namespace
 
+#ifndef OF_HOST_EMULATION  // tests/host_emul/ compiles the kernel above with g++ and launches it itself
 // same tile geometry as lk_tile.cu (16 x 64), so lk_tile_blocks_per_pair sizes the partial sums for both
 cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t stream) {
     if (batch < 1 || batch > 65535 || (size_t)a.H * a.W >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
@@ -271,5 +272,6 @@ cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t 
     }
     return cudaGetLastError();
 }
+#endif  // OF_HOST_EMULATION
 
 }  // namespace ofb

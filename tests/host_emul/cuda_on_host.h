@@ -1,0 +1,106 @@
+// Just enough of the CUDA execution model to run a kernel's SOURCE on the CPU: every CUDA thread of a block is
+// an OS thread, __syncthreads() is a pthread barrier, __shared__ arrays are function-local statics, warp shuffles
+// exchange through a per-warp scratch line.  Blocks run one after the other.  TEST INFRASTRUCTURE ONLY: it lets
+// `pytest -m "not gpu"` check a kernel's indexing and operation order against the oracle without a GPU.
+//
+// Arithmetic intrinsics (__fadd_rn ...) are single IEEE operations here too (volatile keeps g++ from fusing or
+// reassociating; build with -ffp-contract=off), so a kernel that is bit-exact on the host is bit-exact on the
+// device as long as it only uses the operations listed below.
+#pragma once
+#include <cuda_runtime.h>  // vector types (float2, float4, dim3, uint3), host_defines.h
+#include <pthread.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+// host_defines.h makes the CUDA qualifiers vanish without nvcc; __shared__ must become storage that all threads
+// of the block see
+#undef __shared__
+#define __shared__ static
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+
+namespace cuda_on_host {
+constexpr int MAX_THREADS = 1024;
+struct Block {
+    pthread_barrier_t all;
+    pthread_barrier_t warp[MAX_THREADS / 32];
+    double scratch[MAX_THREADS / 32][32];
+};
+inline Block*& block() {
+    static Block* b = nullptr;
+    return b;
+}
+}  // namespace cuda_on_host
+
+static thread_local uint3 threadIdx;
+static thread_local uint3 blockIdx;
+static thread_local dim3 blockDim;
+static thread_local dim3 gridDim;
+
+static inline void __syncthreads() { pthread_barrier_wait(&cuda_on_host::block()->all); }
+static inline double __shfl_down_sync(unsigned, double v, int off) {
+    cuda_on_host::Block* b = cuda_on_host::block();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    b->scratch[w][lane] = v;
+    pthread_barrier_wait(&b->warp[w]);
+    const double r = lane + off < 32 ? b->scratch[w][lane + off] : v;
+    pthread_barrier_wait(&b->warp[w]);
+    return r;
+}
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+
+namespace cuda_on_host {
+// kernel(args) for every thread of every block of `grid`, `threads` threads per block (multiple of 32)
+template <typename Kernel>
+void launch(dim3 grid, int threads, Kernel kernel) {
+    Block blk;
+    block() = &blk;
+    pthread_barrier_init(&blk.all, nullptr, threads);
+    for (int w = 0; w < threads / 32; ++w) pthread_barrier_init(&blk.warp[w], nullptr, 32);
+    struct Arg {
+        int tid, threads;
+        dim3 grid;
+        Kernel* k;
+    };
+    std::vector<Arg> args(threads);
+    std::vector<pthread_t> tids(threads);
+    auto body = [](void* p) -> void* {
+        Arg* a = static_cast<Arg*>(p);
+        blockDim = dim3(a->threads, 1, 1);
+        gridDim = a->grid;
+        threadIdx = uint3{(unsigned)a->tid, 0, 0};
+        for (unsigned z = 0; z < a->grid.z; ++z)
+            for (unsigned y = 0; y < a->grid.y; ++y)
+                for (unsigned x = 0; x < a->grid.x; ++x) {
+                    blockIdx = uint3{x, y, z};
+                    (*a->k)();
+                    pthread_barrier_wait(&block()->all);  // the next block reuses the static "shared memory"
+                }
+        return nullptr;
+    };
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    for (int t = 0; t < threads; ++t) {
+        args[t] = Arg{t, threads, grid, &kernel};
+        pthread_create(&tids[t], &attr, body, &args[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(tids[t], nullptr);
+    pthread_attr_destroy(&attr);
+    pthread_barrier_destroy(&blk.all);
+    for (int w = 0; w < threads / 32; ++w) pthread_barrier_destroy(&blk.warp[w]);
+    block() = nullptr;
+}
+}  // namespace cuda_on_host
