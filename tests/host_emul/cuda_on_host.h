@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>  // vector types (float2, float4, dim3, uint3), host_defines.h
 #include <pthread.h>
 
+#include <cfenv>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -57,6 +58,32 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fadd_rd(float a, float b) {  // round toward -infinity (build with -frounding-math)
+    const int mode = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile float x = a, y = b;
+    volatile float r = x + y;
+    fesetround(mode);
+    return r;
+}
+static inline int __float_as_int(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
+static inline void __stcs(float* p, float v) { *p = v; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline bool __all_sync(unsigned, bool pred) {
+    cuda_on_host::Block* b = cuda_on_host::block();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    b->scratch[w][lane] = pred ? 1.0 : 0.0;
+    pthread_barrier_wait(&b->warp[w]);
+    bool all = true;
+    for (int l = 0; l < 32; ++l) all = all && b->scratch[w][l] != 0.0;
+    pthread_barrier_wait(&b->warp[w]);
+    return all;
+}
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
