@@ -1,7 +1,7 @@
 // warp_image on the device for the split refinement iteration (python/lucas_kanade_pyramidal.py:66-97):
 // the sample / blend helpers and warp_rows_kernel<F>.  Included by lk_march.cu (which launches the kernel) and,
 // compiled by g++ on top of tests/host_emul/cuda_on_host.h, by the CPU test that runs this source against the
-// oracle's warp_image.
+// reference's warp_image.
 #pragma once
 #include "of_common.cuh"
 
