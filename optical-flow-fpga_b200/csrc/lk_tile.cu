@@ -102,7 +102,7 @@ __device__ __forceinline__ float np_finish(const NpAcc<WIN>& s) {
 
 template <int SRC, int WIN>
 __global__ void __launch_bounds__(TILE_THREADS, WIN <= 5 ? (SRC == SRC_WARPED ? 3 : 2) : 1) lk_tile_kernel(TileArgs a) {
-    extern __shared__ float smem[];
+    OF_DYNAMIC_SMEM(float, smem);
     constexpr bool FLOW = (SRC == SRC_WARP || SRC == SRC_WARPED);  // refinement iteration: flow_out = flow_in + d
     constexpr bool GATHER = (SRC == SRC_WARP);                     // stage A gathers the current frame itself
     constexpr int HW = WIN / 2;
@@ -387,6 +387,7 @@ __global__ void convergence_update_kernel(const double* __restrict__ sums, int b
     if (mu < OF_CONVERGENCE_EPS && mv < OF_CONVERGENCE_EPS) done[pair] = 1;
 }
 
+#ifndef OF_HOST_EMULATION  // tests/host_emul/ compiles the kernels above with g++ and launches them itself
 cudaError_t launch_convergence_update(const double* sums, int batch, double n_pixels, int* sel, int* done,
                                       int* iters_executed, float* residuals, int max_iters, int iteration,
                                       int* launches, cudaStream_t stream) {
@@ -462,5 +463,6 @@ cudaError_t launch_iter_finalize(const IterFinalizeArgs& a, int batch, int* laun
     iter_finalize_kernel<<<batch, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
+#endif  // OF_HOST_EMULATION
 
 }  // namespace ofb

@@ -11,6 +11,11 @@
 #define OF_DET_EPS 1e-4f          // lucas_kanade_core.py:131
 #define OF_CONVERGENCE_EPS 0.01f  // lucas_kanade_pyramidal.py:221
 
+// the kernel's dynamic shared memory as an array `name` of `type` (tests/host_emul/ points it at a host buffer)
+#ifndef OF_DYNAMIC_SMEM
+#define OF_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 namespace ofb {
 
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }

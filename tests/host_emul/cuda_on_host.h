@@ -35,7 +35,13 @@ inline Block*& block() {
     static Block* b = nullptr;
     return b;
 }
+// dynamic shared memory of the kernel being emulated (set by the harness before launch)
+inline void*& dynamic_smem() {
+    static void* p = nullptr;
+    return p;
+}
 }  // namespace cuda_on_host
+#define OF_DYNAMIC_SMEM(type, name) type* name = static_cast<type*>(cuda_on_host::dynamic_smem())
 
 static thread_local uint3 threadIdx;
 static thread_local uint3 blockIdx;

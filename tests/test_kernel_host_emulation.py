@@ -1,7 +1,8 @@
-"""Exact-mode kernels run ON THE CPU from their own source files: lk_tile5_kernel (the default for window 5) and
-warp_rows_kernel<double> / <float> (warp_image of the split refinement iteration).
+"""Exact-mode kernels run ON THE CPU from their own source files: lk_tile5_kernel (the default for window 5),
+lk_tile_kernel (every window; frames, gradients, in-tile warp), iter_finalize_kernel, and warp_rows_kernel<double> /
+<float> (warp_image of the split refinement iteration).
 
-tests/host_emul/emul_*.cpp #include optical-flow-fpga_b200/csrc/lk_tile5.cu / warp_rows.cuh and compile them with
+tests/host_emul/emul_*.cpp #include optical-flow-fpga_b200/csrc/lk_tile5.cu / lk_tile.cu / warp_rows.cuh and compile them with
 g++ on top of tests/host_emul/cuda_on_host.h (every CUDA thread of a block is an OS thread, __syncthreads() a barrier,
 __shared__ arrays statics, warp votes / shuffles exchanges through a scratch line, the *_rn / *_rd intrinsics single
 IEEE operations).  What the GPU tests establish on the device
@@ -28,34 +29,39 @@ f32 = np.float32
 _vp, _i = C.c_void_p, C.c_int
 
 
-@pytest.fixture(scope="module")
-def emul(tmp_path_factory):
+def _build(tmp_path_factory, name):
     gxx = shutil.which("g++")
     if gxx is None or not (CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("needs g++ and the CUDA headers (vector types only; nothing CUDA is linked or run)")
-    out = tmp_path_factory.mktemp("host_emul") / "libemul_lk_tile5.so"
-    cmd = [gxx, "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-DOF_HOST_EMULATION",
-           "-I", str(CSRC), "-I", str(CUDA_INC), str(ROOT / "tests" / "host_emul" / "emul_lk_tile5.cpp"), "-o", str(out)]
+    out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
+    cmd = [gxx, "-O1", "-ffp-contract=off", "-frounding-math", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w",
+           "-DOF_HOST_EMULATION", "-I", str(CSRC), "-I", str(CUDA_INC), str(ROOT / "tests" / "host_emul" / f"{name}.cpp"),
+           "-o", str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
-    lib = C.CDLL(str(out))
+    return C.CDLL(str(out))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    lib = _build(tmp_path_factory, "emul_lk_tile5")
     lib.emul_lk_tile5_frames.argtypes = [_vp] * 4 + [_i] * 3
     lib.emul_lk_tile5_warped.argtypes = [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
     return lib
 
 
 @pytest.fixture(scope="module")
+def emul_v1(tmp_path_factory):
+    lib = _build(tmp_path_factory, "emul_lk_tile")
+    lib.emul_lk_tile.argtypes = [_i, _i] + [_vp] * 5 + [_i] * 3
+    lib.emul_lk_tile_refine.argtypes = [_i, _i] + [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
+    lib.emul_iter_finalize.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, C.c_long, _i, _i]
+    return lib
+
+
+@pytest.fixture(scope="module")
 def emul_warp(tmp_path_factory):
-    gxx = shutil.which("g++")
-    if gxx is None or not (CUDA_INC / "cuda_runtime.h").exists():
-        pytest.skip("needs g++ and the CUDA headers (vector types only; nothing CUDA is linked or run)")
-    out = tmp_path_factory.mktemp("host_emul_warp") / "libemul_warp_rows.so"
-    cmd = [gxx, "-O1", "-ffp-contract=off", "-frounding-math", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w",
-           "-DOF_HOST_EMULATION", "-I", str(CSRC), "-I", str(CUDA_INC),
-           str(ROOT / "tests" / "host_emul" / "emul_warp_rows.cpp"), "-o", str(out)]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr[-3000:]
-    lib = C.CDLL(str(out))
+    lib = _build(tmp_path_factory, "emul_warp_rows")
     lib.emul_warp_rows.argtypes = [_vp] * 4 + [_i] * 6
     return lib
 
@@ -214,3 +220,90 @@ def test_warp_rows_row_range(emul_warp):
     ref = orc.warp_image(img, fu, fv)
     assert np.array_equal(bits(got[7:19]), bits(ref[7:19]))
     assert np.isnan(got[:7]).all() and np.isnan(got[19:]).all()
+
+
+# ---------------------------------------------------------------------------------------
+# lk_tile_kernel (first exact kernel: every window, gradients, in-tile warp) and the iteration loop
+# ---------------------------------------------------------------------------------------
+SRC_FRAMES, SRC_WARP, SRC_GRADS, SRC_WARPED = 0, 1, 2, 3
+
+
+@pytest.mark.parametrize("w", [1, 3, 5, 7, 9, 11])
+def test_first_tile_kernel_source_on_cpu_every_window(emul_v1, w):
+    rng = np.random.default_rng(w)
+    shape = (2, 27, 75)
+    a = (rng.standard_normal(shape) * 50).astype(f32)
+    b = (a + rng.standard_normal(shape) * 3).astype(f32)
+    u, v = np.full_like(a, np.nan), np.full_like(a, np.nan)
+    assert emul_v1.emul_lk_tile(SRC_FRAMES, w, ptr(a), ptr(b), None, ptr(u), ptr(v), 2, shape[1], shape[2]) == 0
+    for k in range(2):
+        uo, vo = orc.lucas_kanade_single_scale(a[k], b[k], w)
+        assert np.array_equal(bits(u[k]), bits(uo)) and np.array_equal(bits(v[k]), bits(vo)), f"pair {k}"
+    # the same windows from gradient planes (lucas_kanade_from_gradients)
+    ix, iy, it = (rng.standard_normal(shape[1:]).astype(f32) for _ in range(3))
+    u1, v1 = np.full_like(ix, np.nan), np.full_like(ix, np.nan)
+    assert emul_v1.emul_lk_tile(SRC_GRADS, w, ptr(ix), ptr(iy), ptr(it), ptr(u1), ptr(v1), 1, shape[1], shape[2]) == 0
+    uo, vo = orc.lucas_kanade_from_gradients(ix, iy, it, w)
+    assert np.array_equal(bits(u1), bits(uo)) and np.array_equal(bits(v1), bits(vo))
+
+
+def _level_loop(emul_v1, emul_warp, emul5, prev, curr, iters, form):
+    """The exact-mode iteration loop of one pyramid level as of_api.cu's driver runs it, kernel by kernel:
+    form 'fused' = lk_tile_kernel<SRC_WARP>; 'split' = warp_rows_kernel<double> + lk_tile5_kernel<SRC_WARPED>;
+    'split_v1' = warp_rows_kernel<double> + lk_tile_kernel<SRC_WARPED>.  Then iter_finalize_kernel."""
+    B, H, W = prev.shape
+    start = iters & 1
+    bu = [np.zeros((B, H, W), f32), np.zeros((B, H, W), f32)]
+    bv = [np.zeros((B, H, W), f32), np.zeros((B, H, W), f32)]
+    sel = np.zeros(B, np.int32)
+    done = np.zeros(B, np.int32)
+    executed = np.zeros(B, np.int32)
+    resid = np.zeros((B, iters, 2), f32)
+    nblk = ((W + 63) // 64) * ((H + 15) // 16)
+    partial = np.zeros((B, nblk, 2))
+    warped = np.zeros((B, H, W), f32)
+    for it in range(iters):
+        if form == "fused":
+            emul_v1.emul_lk_tile_refine(SRC_WARP, 5, ptr(prev), ptr(curr), ptr(bu[0]), ptr(bv[0]), ptr(bu[1]), ptr(bv[1]),
+                                        ptr(sel), start, ptr(done), ptr(partial), B, H, W, 0, H, 0, H)
+        else:
+            for b in range(B):
+                if not done[b]:
+                    cur = sel[b] ^ start
+                    emul_warp.emul_warp_rows(ptr(curr[b]), ptr(bu[cur][b]), ptr(bv[cur][b]), ptr(warped[b]), 1, H, W, 0, H, 1)
+            if form == "split":
+                emul5.emul_lk_tile5_warped(ptr(prev), ptr(warped), ptr(bu[0]), ptr(bv[0]), ptr(bu[1]), ptr(bv[1]), ptr(sel),
+                                           start, ptr(done), ptr(partial), B, H, W, 0, H, 0, H)
+            else:
+                emul_v1.emul_lk_tile_refine(SRC_WARPED, 5, ptr(prev), ptr(warped), ptr(bu[0]), ptr(bv[0]), ptr(bu[1]),
+                                            ptr(bv[1]), ptr(sel), start, ptr(done), ptr(partial), B, H, W, 0, H, 0, H)
+        emul_v1.emul_iter_finalize(ptr(partial), nblk, H, W, ptr(sel), ptr(done), ptr(executed), 1, ptr(resid), iters * 2,
+                                   it, B)
+    out_u = np.stack([bu[sel[b] ^ start][b] for b in range(B)])
+    out_v = np.stack([bv[sel[b] ^ start][b] for b in range(B)])
+    return out_u, out_v, executed, resid
+
+
+@pytest.mark.parametrize("form", ["fused", "split", "split_v1"])
+def test_exact_iteration_loop_source_on_cpu_equals_oracle(emul_v1, emul_warp, emul, form):
+    """One level, three iterations, three pairs: a moving pair, a pair with sub-pixel motion of the other sign, and a
+    pair without motion that must stop after its first iteration (the reference's early exit) while the others go on."""
+    from scipy.ndimage import gaussian_filter, shift
+
+    rng = np.random.default_rng(33)
+    H, W = 40, 90
+    base = gaussian_filter((rng.random((3, H, W)) * 255).astype(f32), (0, 1.5, 1.5)).astype(f32)
+    prev = base.copy()
+    curr = np.stack([shift(base[0], (0.4, -0.7), order=1, mode="nearest"), shift(base[1], (-0.3, 0.2), order=1, mode="nearest"),
+                     base[2]]).astype(f32)
+    u, v, executed, resid = _level_loop(emul_v1, emul_warp, emul, prev, curr, 3, form)
+    for b in range(3):
+        trace = []
+        uo, vo = orc.lucas_kanade_pyramidal(prev[b], curr[b], 1, 5, 3, trace=trace)
+        assert np.array_equal(bits(u[b]), bits(uo)), f"u, pair {b}"
+        assert np.array_equal(bits(v[b]), bits(vo)), f"v, pair {b}"
+        assert executed[b] == len(trace)
+        for (_, it, mu, mv) in trace:  # float64 sums vs the reference's float32 pairwise mean
+            assert resid[b, it, 0] == pytest.approx(mu, rel=1e-5, abs=1e-9)
+            assert resid[b, it, 1] == pytest.approx(mv, rel=1e-5, abs=1e-9)
+    assert executed.tolist() == [3, 3, 1]
