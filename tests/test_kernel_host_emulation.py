@@ -152,6 +152,29 @@ def test_refinement_iteration_source_on_cpu_equals_oracle(emul, rows):
     assert (buf_u[1][2] == 123.0).all() and np.isnan(partial[2]).all()  # converged pair untouched
 
 
+def test_refinement_band_needs_the_warped_plane_on_three_halo_rows_only(emul):
+    """Row-band use of the split form: warp_rows_kernel has to cover rows [row_lo - 3, row_hi + 3) (window // 2 + 1
+    for the Sobel tap); whatever lies outside -- here NaN -- must not reach the rows that are written."""
+    rng = np.random.default_rng(5)
+    H, W = 64, 100
+    prev = (rng.random((1, H, W)) * 255).astype(f32)
+    warped_full = (prev + rng.standard_normal((1, H, W))).astype(f32)
+    fu = rng.standard_normal((1, H, W)).astype(f32)
+    fv = rng.standard_normal((1, H, W)).astype(f32)
+    row_lo, row_hi = 18, 41
+    warped = np.full_like(warped_full, np.nan)
+    warped[:, row_lo - 3:row_hi + 3] = warped_full[:, row_lo - 3:row_hi + 3]
+    out_u, out_v = np.full_like(fu, 7.0), np.full_like(fv, 7.0)
+    nblk = ((W + 63) // 64) * ((row_hi - row_lo + 15) // 16)
+    partial = np.zeros((1, nblk, 2))
+    emul.emul_lk_tile5_warped(ptr(prev), ptr(warped), ptr(fu), ptr(fv), ptr(out_u), ptr(out_v), None, 0, None, ptr(partial),
+                              1, H, W, row_lo, row_hi, row_lo, row_hi)
+    du, dv = orc.lucas_kanade_single_scale(prev[0], warped_full[0], 5)
+    assert np.array_equal(bits(out_u[0, row_lo:row_hi]), bits((fu[0] + du)[row_lo:row_hi]))
+    assert np.array_equal(bits(out_v[0, row_lo:row_hi]), bits((fv[0] + dv)[row_lo:row_hi]))
+    assert np.isfinite(partial).all()
+
+
 # ---------------------------------------------------------------------------------------
 # warp_rows_kernel
 # ---------------------------------------------------------------------------------------
