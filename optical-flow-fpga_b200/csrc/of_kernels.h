@@ -14,6 +14,11 @@ struct SmemOptIn {
     std::atomic<unsigned long long> done{0};  // one bit per device ordinal
     template <typename Kernel>
     cudaError_t ensure(Kernel kernel, size_t bytes) {
+#ifdef OF_HOST_EMULATION  // tests/host_emul/: no device, nothing to opt in to
+        (void)kernel;
+        (void)bytes;
+        return cudaSuccess;
+#else
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
@@ -22,6 +27,7 @@ struct SmemOptIn {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_relaxed);
         return e;
+#endif
     }
 };
 

@@ -54,7 +54,7 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
                              int W, int* launches, cudaStream_t stream) {
     if (launches) *launches += 1;
     dim3 grid((W + 63) / 64, (H + 3) / 4, batch);
-    gradients_kernel<<<grid, 256, 0, stream>>>(prev, curr, ix, iy, it, H, W);
+    OF_LAUNCH(gradients_kernel, grid, 256, 0, stream, prev, curr, ix, iy, it, H, W);
     return cudaGetLastError();
 }
 
@@ -105,7 +105,7 @@ __device__ __forceinline__ double gauss_tap_sum(const double* x, const double* w
 // output per thread and pass (only sigma != 2 gets here; the reference always uses sigma = 2).
 template <int RADIUS>
 __global__ void __launch_bounds__(256) pyramid_down_kernel(PyrArgs a) {
-    extern __shared__ float smem[];
+    OF_DYNAMIC_SMEM(float, smem);
     constexpr int SEG = PYR_SEG;
     const int H = a.H, W = a.W, r = RADIUS > 0 ? RADIUS : a.radius;
     const float* src = a.src + (size_t)blockIdx.z * H * W;
@@ -263,9 +263,9 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
     if (launches) *launches += 1;
     dim3 grid((ow + a.tile_w - 1) / a.tile_w, (row_hi - row_lo + a.tile_h - 1) / a.tile_h, batch);
     if (which)
-        pyramid_down_kernel<8><<<grid, 256, smem, stream>>>(a);  // sigma = 2, the reference's pyramid
+        OF_LAUNCH(pyramid_down_kernel<8>, grid, 256, smem, stream, a);  // sigma = 2, the reference's pyramid
     else
-        pyramid_down_kernel<0><<<grid, 256, smem, stream>>>(a);
+        OF_LAUNCH(pyramid_down_kernel<0>, grid, 256, smem, stream, a);
     return cudaGetLastError();
 }
 
@@ -288,7 +288,7 @@ cudaError_t launch_warp(const float* img, const float* fu, const float* fv, floa
                         int* launches, cudaStream_t stream) {
     if (launches) *launches += 1;
     dim3 grid((W + 63) / 64, (H + 3) / 4, batch);
-    warp_kernel<<<grid, 256, 0, stream>>>(img, fu, fv, out, H, W);
+    OF_LAUNCH(warp_kernel, grid, 256, 0, stream, img, fu, fv, out, H, W);
     return cudaGetLastError();
 }
 
@@ -494,9 +494,9 @@ cudaError_t launch_upsample_flow(const float* cu0, const float* cv0, const float
     dim3 grid((tw + 255) / 256, (row_hi - row_lo + UP_ROWS - 1) / UP_ROWS, batch);
     // the staged tile covers 16 target rows x 256 target columns when the grid steps are <= ~0.5
     if (15.0 * a.step_y + 1.0 < UPS_CR - 1 && 255.0 * a.step_x + 1.0 < UPS_CC - 1)
-        upsample_flow_tile_kernel<<<grid, 256, 0, stream>>>(a);
+        OF_LAUNCH(upsample_flow_tile_kernel, grid, 256, 0, stream, a);
     else
-        upsample_flow_kernel<<<grid, 256, 0, stream>>>(a);
+        OF_LAUNCH(upsample_flow_kernel, grid, 256, 0, stream, a);
     return cudaGetLastError();
 }
 
@@ -524,7 +524,7 @@ cudaError_t launch_select_copy(const float* u0, const float* v0, const float* u1
     if (bx < 1) bx = 1;
     if (bx > 4096) bx = 4096;
     dim3 grid(bx, batch);
-    select_copy_kernel<<<grid, 256, 0, stream>>>(u0, v0, u1, v1, sel, sel_xor, out_u, out_v, n);
+    OF_LAUNCH(select_copy_kernel, grid, 256, 0, stream, u0, v0, u1, v1, sel, sel_xor, out_u, out_v, n);
     return cudaGetLastError();
 }
 

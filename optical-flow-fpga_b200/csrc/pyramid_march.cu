@@ -81,7 +81,7 @@ __device__ __forceinline__ double pm_gauss(const double* x, const double* w) {
 
 template <bool FMA>
 __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrMarchArgs a) {
-    extern __shared__ __align__(16) unsigned char pm_smem[];
+    OF_DYNAMIC_SMEM_ALIGNED(16, unsigned char, pm_smem);
     // axis-0 results of two consecutive steps, already rounded to float32 but kept as float64 so
     // that the axis-1 pass needs no conversions; then the ring of fully smoothed rows (float32)
     double* tmp = reinterpret_cast<double*>(pm_smem);                               // [2][PM_CH][PM_TPITCH]
@@ -261,9 +261,9 @@ cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H,
     if (launches) *launches += 1;
     dim3 grid(n_strips, n_bands, batch);
     if (fused_multiply_add)
-        pyramid_march_kernel<true><<<grid, PM_THREADS, PM_SMEM_BYTES, stream>>>(a);
+        OF_LAUNCH(pyramid_march_kernel<true>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
     else
-        pyramid_march_kernel<false><<<grid, PM_THREADS, PM_SMEM_BYTES, stream>>>(a);
+        OF_LAUNCH(pyramid_march_kernel<false>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
     return cudaGetLastError();
 }
 

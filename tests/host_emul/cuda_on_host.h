@@ -42,6 +42,11 @@ inline void*& dynamic_smem() {
 }
 }  // namespace cuda_on_host
 #define OF_DYNAMIC_SMEM(type, name) type* name = static_cast<type*>(cuda_on_host::dynamic_smem())
+#define OF_DYNAMIC_SMEM_ALIGNED(align, type, name) type* name = static_cast<type*>(cuda_on_host::dynamic_smem())
+// launchers written with OF_LAUNCH (of_common.cuh) run unchanged: grid / block / dynamic shared memory as given
+#define OF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    cuda_on_host::launch_dynamic(grid, block, smem, [&]() { kernel(__VA_ARGS__); })
+#define cudaGetLastError() cudaSuccess
 
 static thread_local uint3 threadIdx;
 static thread_local uint3 blockIdx;
@@ -135,5 +140,14 @@ void launch(dim3 grid, int threads, Kernel kernel) {
     pthread_barrier_destroy(&blk.all);
     for (int w = 0; w < threads / 32; ++w) pthread_barrier_destroy(&blk.warp[w]);
     block() = nullptr;
+}
+template <typename Kernel>
+void launch_dynamic(dim3 grid, dim3 block, size_t smem_bytes, Kernel kernel) {
+    std::vector<double> buf(smem_bytes / sizeof(double) + 2);  // 16-byte aligned is all a kernel may assume
+    void* p = buf.data();
+    if (reinterpret_cast<uintptr_t>(p) & 15) p = static_cast<char*>(p) + 8;
+    dynamic_smem() = p;
+    launch(grid, (int)block.x, kernel);
+    dynamic_smem() = nullptr;
 }
 }  // namespace cuda_on_host

@@ -1,6 +1,7 @@
 """Exact-mode kernels run ON THE CPU from their own source files: lk_tile5_kernel (the default for window 5),
-lk_tile_kernel (every window; frames, gradients, in-tile warp), iter_finalize_kernel, and warp_rows_kernel<double> /
-<float> (warp_image of the split refinement iteration).
+lk_tile_kernel (every window; frames, gradients, in-tile warp), iter_finalize_kernel, warp_rows_kernel<double> /
+<float> (warp_image of the split refinement iteration), and pyramid.cu / pyramid_march.cu with their launchers
+(gradients, both Gaussian-pyramid kernels, warp_kernel, both upsample kernels).
 
 tests/host_emul/emul_*.cpp #include optical-flow-fpga_b200/csrc/lk_tile5.cu / lk_tile.cu / warp_rows.cuh and compile them with
 g++ on top of tests/host_emul/cuda_on_host.h (every CUDA thread of a block is an OS thread, __syncthreads() a barrier,
@@ -29,14 +30,14 @@ f32 = np.float32
 _vp, _i = C.c_void_p, C.c_int
 
 
-def _build(tmp_path_factory, name):
+def _build(tmp_path_factory, name, *more):
     gxx = shutil.which("g++")
     if gxx is None or not (CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("needs g++ and the CUDA headers (vector types only; nothing CUDA is linked or run)")
     out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
+    srcs = [str(ROOT / "tests" / "host_emul" / f"{n}.cpp") for n in (name,) + more]
     cmd = [gxx, "-O1", "-ffp-contract=off", "-frounding-math", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w",
-           "-DOF_HOST_EMULATION", "-I", str(CSRC), "-I", str(CUDA_INC), str(ROOT / "tests" / "host_emul" / f"{name}.cpp"),
-           "-o", str(out)]
+           "-DOF_HOST_EMULATION", "-I", str(CSRC), "-I", str(CUDA_INC), *srcs, "-o", str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     return C.CDLL(str(out))
@@ -56,6 +57,16 @@ def emul_v1(tmp_path_factory):
     lib.emul_lk_tile.argtypes = [_i, _i] + [_vp] * 5 + [_i] * 3
     lib.emul_lk_tile_refine.argtypes = [_i, _i] + [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
     lib.emul_iter_finalize.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, C.c_long, _i, _i]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def emul_pyr(tmp_path_factory):
+    lib = _build(tmp_path_factory, "emul_pyramid", "emul_pyramid_march")
+    lib.emul_pyramid_down.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i]
+    lib.emul_gradients.argtypes = [_vp] * 5 + [_i] * 3
+    lib.emul_warp.argtypes = [_vp] * 4 + [_i] * 3
+    lib.emul_upsample_flow.argtypes = [_vp] * 4 + [_i] * 7
     return lib
 
 
@@ -330,3 +341,72 @@ def test_exact_iteration_loop_source_on_cpu_equals_oracle(emul_v1, emul_warp, em
             assert resid[b, it, 0] == pytest.approx(mu, rel=1e-5, abs=1e-9)
             assert resid[b, it, 1] == pytest.approx(mv, rel=1e-5, abs=1e-9)
     assert executed.tolist() == [3, 3, 1]
+
+
+# ---------------------------------------------------------------------------------------
+# pyramid.cu / pyramid_march.cu through their own launchers
+# ---------------------------------------------------------------------------------------
+def run_pyramid_down(lib, img, rows=None, fast=False):
+    wts = orc.gaussian_weights(2.0)
+    b, h, w = img.shape
+    oh, ow = h // 2, w // 2
+    out = np.full((b, oh, ow), np.nan, f32)
+    lo, hi = rows if rows else (0, oh)
+    assert lib.emul_pyramid_down(ptr(img), ptr(out), b, h, w, oh, ow, ptr(wts), (len(wts) - 1) // 2, lo, hi, int(fast)) == 0
+    return out
+
+
+def test_pyramid_kernels_source_on_cpu_random_shapes(emul_pyr):
+    """One pyramid level (gaussian_filter sigma 2 + bilinear decimation) for 40 random shapes: the marching kernel
+    (>= 16 x 248; strips of 240 columns, bands planned per launch) and the tile kernel (everything smaller),
+    chosen by launch_pyramid_down exactly as on the device."""
+    rng = np.random.default_rng(17)
+    shapes = [(16, 248), (16, 247), (8, 8), (2, 2), (3, 9), (45, 67), (17, 249), (64, 481), (31, 720), (130, 250)]
+    while len(shapes) < 40:
+        shapes.append((int(rng.integers(2, 120)), int(rng.integers(2, 700))))
+    for h, w in shapes:
+        img = (rng.random((1, h, w)) * 255).astype(f32)
+        got = run_pyramid_down(emul_pyr, img)
+        want = orc.build_gaussian_pyramid(img[0], 2)[0]
+        assert np.array_equal(bits(got[0]), bits(want)), (h, w)
+
+
+def test_pyramid_march_batch_row_range_and_fma_flavour(emul_pyr):
+    rng = np.random.default_rng(3)
+    img = (rng.random((3, 96, 530)) * 255).astype(f32)
+    want = np.stack([orc.build_gaussian_pyramid(img[b], 2)[0] for b in range(3)])
+    assert np.array_equal(bits(run_pyramid_down(emul_pyr, img)), bits(want))
+    part = run_pyramid_down(emul_pyr, img, rows=(11, 37))  # row-band mode: only these coarse rows
+    assert np.array_equal(bits(part[:, 11:37]), bits(want[:, 11:37]))
+    assert np.isnan(part[:, :11]).all() and np.isnan(part[:, 37:]).all()
+    fma = run_pyramid_down(emul_pyr, img, fast=True)  # fast mode: fused multiply-adds, last-bit differences only
+    assert np.abs(fma - want).max() <= np.spacing(f32(255.0))
+    assert (bits(fma) != bits(want)).mean() < 1e-3
+
+
+def test_gradients_warp_upsample_launchers_source_on_cpu(emul_pyr):
+    rng = np.random.default_rng(12)
+    for h, w in [(5, 7), (33, 100), (64, 257)]:
+        p = (rng.standard_normal((2, h, w)) * 50).astype(f32)
+        c = (p + rng.standard_normal((2, h, w))).astype(f32)
+        ix, iy, it = (np.full_like(p, np.nan) for _ in range(3))
+        assert emul_pyr.emul_gradients(ptr(p), ptr(c), ptr(ix), ptr(iy), ptr(it), 2, h, w) == 0
+        for b in range(2):
+            for got, want in zip((ix[b], iy[b], it[b]), orc.compute_gradients(p[b], c[b])):
+                assert np.array_equal(bits(got), bits(want))
+        fu = (rng.standard_normal((2, h, w)) * 2).astype(f32)
+        fv = (rng.standard_normal((2, h, w)) * 1e-6).astype(f32)  # tiny: the rounded float64 coordinate sum
+        out = np.full_like(p, np.nan)
+        assert emul_pyr.emul_warp(ptr(p), ptr(fu), ptr(fv), ptr(out), 2, h, w) == 0
+        for b in range(2):
+            assert np.array_equal(bits(out[b]), bits(orc.warp_image(p[b], fu[b], fv[b])))
+    # upsample_flow: the tile kernel (true upsampling, step <= ~0.5) and the generic kernel (any other ratio)
+    for (ch, cw), (th, tw) in [((20, 31), (40, 62)), ((20, 31), (41, 63)), ((33, 40), (33, 40)), ((30, 50), (12, 21)),
+                               ((7, 300), (15, 601)), ((1, 5), (3, 9))]:
+        cu = (rng.standard_normal((2, ch, cw)) * 3).astype(f32)
+        cv = (rng.standard_normal((2, ch, cw)) * 3).astype(f32)
+        fu, fv = np.full((2, th, tw), np.nan, f32), np.full((2, th, tw), np.nan, f32)
+        assert emul_pyr.emul_upsample_flow(ptr(cu), ptr(cv), ptr(fu), ptr(fv), 2, ch, cw, th, tw, 0, th) == 0
+        for b in range(2):
+            wu, wv = orc.upsample_flow(cu[b], cv[b], (th, tw))
+            assert np.array_equal(bits(fu[b]), bits(wu)) and np.array_equal(bits(fv[b]), bits(wv)), ((ch, cw), (th, tw))
