@@ -111,7 +111,7 @@ cudaError_t launch_lk_fixed(const uint8_t* prev, const uint8_t* curr, int16_t* u
     if (batch > 65535) return cudaErrorInvalidValue;
     if (launches) *launches += 1;
     dim3 grid((W + FTX - 1) / FTX, (H + FTY - 1) / FTY, batch);
-    lk_fixed_kernel<<<grid, 256, 0, stream>>>(prev, curr, u, v, H, W, mirror_avg_quirk);
+    OF_LAUNCH(lk_fixed_kernel, grid, 256, 0, stream, prev, curr, u, v, H, W, mirror_avg_quirk);
     return cudaGetLastError();
 }
 

@@ -137,10 +137,10 @@ cudaError_t launch_flow_metrics(const float* u, const float* v, const float* u_t
     a.partial = partial;
     if (launches) *launches += 2;
     dim3 grid(a.blocks_per_pair, batch);
-    metrics_partial_kernel<<<grid, MET_THREADS, 0, stream>>>(a);
+    OF_LAUNCH(metrics_partial_kernel, grid, MET_THREADS, 0, stream, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    metrics_final_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(a, out, batch);
+    OF_LAUNCH(metrics_final_kernel, (batch + 127) / 128, 128, 0, stream, a, out, batch);
     return cudaGetLastError();
 }
 

@@ -104,7 +104,7 @@ cudaError_t launch_warp_affine(const uint8_t* src, uint8_t* dst, const double* m
             for (int k = 0; k < 6; ++k) a.minv[b][k] = minv[(size_t)(b0 + b) * 6 + k];
         if (launches) *launches += 1;
         dim3 grid((W + 255) / 256, H, nb);
-        warp_affine_kernel<<<grid, 256, 0, stream>>>(a);
+        OF_LAUNCH(warp_affine_kernel, grid, 256, 0, stream, a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -116,7 +116,7 @@ cudaError_t launch_apply_motion(const uint8_t* src, uint8_t* dst, const double* 
     if (batch < 1 || batch > 65535 || H < 1 || H > 65535 || W < 1) return cudaErrorInvalidValue;
     if (launches) *launches += 1;
     dim3 grid((W + 255) / 256, H, batch);
-    apply_motion_kernel<<<grid, 256, 0, stream>>>(src, dst, dx, dy, H, W, cval);
+    OF_LAUNCH(apply_motion_kernel, grid, 256, 0, stream, src, dst, dx, dy, H, W, cval);
     return cudaGetLastError();
 }
 

@@ -16,10 +16,6 @@
 #define OF_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
 #define OF_DYNAMIC_SMEM_ALIGNED(align, type, name) extern __shared__ __align__(align) type name[]
 #endif
-// a kernel launch (tests/host_emul/ runs the kernel's threads as OS threads instead)
-#ifndef OF_LAUNCH
-#define OF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
-#endif
 
 namespace ofb {
 

@@ -8,6 +8,11 @@
 
 namespace ofb {
 
+// a kernel launch (tests/host_emul/ runs the kernel's threads as OS threads instead)
+#ifndef OF_LAUNCH
+#define OF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 // Opt-in to more than 48 KB of dynamic shared memory, once per (kernel, device): the attribute
 // belongs to the device's context, so a process that drives several GPUs sets it on each.
 struct SmemOptIn {

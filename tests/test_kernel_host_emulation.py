@@ -1,7 +1,8 @@
 """Exact-mode kernels run ON THE CPU from their own source files: lk_tile5_kernel (the default for window 5),
 lk_tile_kernel (every window; frames, gradients, in-tile warp), iter_finalize_kernel, warp_rows_kernel<double> /
-<float> (warp_image of the split refinement iteration), and pyramid.cu / pyramid_march.cu with their launchers
-(gradients, both Gaussian-pyramid kernels, warp_kernel, both upsample kernels).
+<float> (warp_image of the split refinement iteration), pyramid.cu / pyramid_march.cu with their launchers
+(gradients, both Gaussian-pyramid kernels, warp_kernel, both upsample kernels), and motion.cu, lk_fixed.cu, metrics.cu
+(the fixture generators' warps, the RTL's integer datapath, the verifier's metrics).
 
 tests/host_emul/emul_*.cpp #include optical-flow-fpga_b200/csrc/lk_tile5.cu / lk_tile.cu / warp_rows.cuh and compile them with
 g++ on top of tests/host_emul/cuda_on_host.h (every CUDA thread of a block is an OS thread, __syncthreads() a barrier,
@@ -21,7 +22,10 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from oracle import flow_metrics_oracle as fmo
+from oracle import lk_fixed_oracle as fxo
 from oracle import lk_float_oracle as orc
+from oracle import pattern_oracle as pto
 
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "optical-flow-fpga_b200" / "csrc"
@@ -410,3 +414,78 @@ def test_gradients_warp_upsample_launchers_source_on_cpu(emul_pyr):
         for b in range(2):
             wu, wv = orc.upsample_flow(cu[b], cv[b], (th, tw))
             assert np.array_equal(bits(fu[b]), bits(wu)) and np.array_equal(bits(fv[b]), bits(wv)), ((ch, cw), (th, tw))
+
+
+# ---------------------------------------------------------------------------------------
+# motion.cu, lk_fixed.cu, metrics.cu
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul_motion(tmp_path_factory):
+    lib = _build(tmp_path_factory, "emul_motion")
+    lib.emul_apply_motion.argtypes = [_vp] * 4 + [_i] * 3 + [C.c_double]
+    lib.emul_warp_affine.argtypes = [_vp] * 3 + [_i] * 4
+    return lib
+
+
+def test_fixture_generator_warps_source_on_cpu(emul_motion):
+    """apply_motion (scipy.ndimage.shift, order 1, constant 128) and apply_motion_opencv (cv2.warpAffine's fixed-point
+    bilinear warp) against the pattern oracle, which tests/golden/motion.npz pins to the reference's generators."""
+    rng = np.random.default_rng(6)
+    shifts = [(0.0, 0.0), (0.5, -0.25), (-1.75, 2.0), (3.0, 3.0), (-0.001, 0.999), (40.0, 0.0), (0.3, -60.0), (1e-9, -1e-9)]
+    for h, w in [(24, 40), (7, 300), (33, 257)]:
+        src = rng.integers(0, 256, (len(shifts), h, w)).astype(np.uint8)
+        dx = np.array([s[0] for s in shifts])
+        dy = np.array([s[1] for s in shifts])
+        dst = np.zeros_like(src)
+        assert emul_motion.emul_apply_motion(ptr(src), ptr(dst), ptr(dx), ptr(dy), len(shifts), h, w, 128.0) == 0
+        for k, (sx, sy) in enumerate(shifts):
+            assert np.array_equal(dst[k], pto.apply_motion(src[k], sx, sy)), (h, w, sx, sy)
+        params = [(0, 0, 0, 1), (1.5, -0.5, 0, 1), (0, 0, 2.0, 1), (0, 0, -5.0, 1.02), (3.2, 1.1, 0.5, 0.98), (-10, 7, 30, 1.2)]
+        params += [tuple(rng.uniform(-4, 4, 2)) + (float(rng.uniform(-10, 10)), float(rng.uniform(0.9, 1.1))) for _ in range(50)]
+        mats = [pto.motion_matrix(w, h, *q) for q in params]  # > 48 frames: the launcher splits the batch
+        minv = np.ascontiguousarray(np.stack([pto.invert_affine(m) for m in mats]).reshape(len(mats), 6))
+        src = rng.integers(0, 256, (len(mats), h, w)).astype(np.uint8)
+        dst = np.zeros_like(src)
+        assert emul_motion.emul_warp_affine(ptr(src), ptr(dst), ptr(minv), len(mats), h, w, 128) == 0
+        for k, m in enumerate(mats):
+            assert np.array_equal(dst[k], pto.warp_affine_u8(src[k], m)), (h, w, params[k])
+
+
+@pytest.mark.parametrize("quirk", [True, False])
+def test_fixed_point_tile_kernel_source_on_cpu(tmp_path_factory, quirk):
+    lib = _build(tmp_path_factory, "emul_fixed")
+    lib.emul_lk_fixed.argtypes = [_vp] * 4 + [_i] * 4
+    rng = np.random.default_rng(int(quirk) + 40)
+    for h, w in [(7, 7), (8, 9), (33, 70), (50, 129)]:
+        p8 = rng.integers(0, 256, (2, h, w)).astype(np.uint8)
+        c8 = np.clip(np.roll(p8, 1, axis=2).astype(np.int32) + rng.integers(-3, 4, p8.shape), 0, 255).astype(np.uint8)
+        p8[1], c8[1] = rng.integers(0, 256, (h, w)), rng.integers(0, 256, (h, w))  # unrelated frames: wrap-arounds, clamps
+        u = np.full((2, h, w), 77, np.int16)
+        v = np.full((2, h, w), 77, np.int16)
+        assert lib.emul_lk_fixed(ptr(p8), ptr(c8), ptr(u), ptr(v), 2, h, w, int(quirk)) == 0
+        for b in range(2):
+            uo, vo = fxo.lk_single_scale_fx(p8[b], c8[b], mirror_avg_quirk=quirk)
+            assert np.array_equal(u[b], uo) and np.array_equal(v[b], vo), (h, w, b)
+
+
+def test_metrics_kernels_source_on_cpu(tmp_path_factory):
+    lib = _build(tmp_path_factory, "emul_metrics")
+    lib.emul_metrics_blocks_per_pair.argtypes = [_i, _i]
+    lib.emul_flow_metrics.argtypes = [_vp] * 4 + [_i] * 7 + [_vp, _vp]
+    rng = np.random.default_rng(2)
+    B, H, W = 3, 60, 90
+    truth = np.array([[1.5, -0.5], [0.0, 0.0], [-2.0, 3.0]], f32)
+    u = (truth[:, 0, None, None] + rng.standard_normal((B, H, W)) * 0.3).astype(f32)
+    v = (truth[:, 1, None, None] + rng.standard_normal((B, H, W)) * 0.3).astype(f32)
+    u[1], v[1] = 0.0, 0.0  # no motion in truth and prediction: angular error 0 by definition (flow_metrics.py:143-147)
+    y0, y1, x0, x1 = 10, 50, 5, 85
+    ut, vt = np.ascontiguousarray(truth[:, 0]), np.ascontiguousarray(truth[:, 1])
+    partial = np.zeros((B, lib.emul_metrics_blocks_per_pair(y1 - y0, x1 - x0), 8))
+    out = np.zeros((B, 5))
+    assert lib.emul_flow_metrics(ptr(u), ptr(v), ptr(ut), ptr(vt), B, H, W, y0, y1, x0, x1, ptr(partial), ptr(out)) == 0
+    mask = np.zeros((H, W), bool)
+    mask[y0:y1, x0:x1] = True
+    for b in range(B):
+        want = fmo.all_metrics(u[b], v[b], float(truth[b, 0]), float(truth[b, 1]), mask)
+        for k, name in enumerate(("mae_u", "mae_v", "rmse", "epe", "aae")):
+            assert out[b, k] == pytest.approx(want[name], rel=2e-6, abs=1e-7), (b, name)
