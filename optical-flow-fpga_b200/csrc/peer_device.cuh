@@ -11,6 +11,7 @@
 
 namespace ofb {
 
+#ifndef OF_HOST_EMULATION  // host stand-ins: tests/host_emul/
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -24,6 +25,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 
 // wait until *flag >= seq; false on time-out or when an earlier wait already failed
 __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, int* err,

@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>  // vector types (float2, float4, dim3, uint3), host_defines.h
 #include <pthread.h>
+#include <sched.h>
 
 #include <cfenv>
 #include <cmath>
@@ -54,15 +55,28 @@ static thread_local dim3 blockDim;
 static thread_local dim3 gridDim;
 
 static inline void __syncthreads() { pthread_barrier_wait(&cuda_on_host::block()->all); }
-static inline double __shfl_down_sync(unsigned, double v, int off) {
-    cuda_on_host::Block* b = cuda_on_host::block();
+namespace cuda_on_host {
+// one warp-wide exchange: every lane publishes `v`, then reads lane `src` (its own value when src is out of range)
+template <typename T>
+static inline T warp_exchange(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffles move at most 8 bytes");
+    Block* b = block();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    b->scratch[w][lane] = v;
+    std::memcpy(&b->scratch[w][lane], &v, sizeof(T));
     pthread_barrier_wait(&b->warp[w]);
-    const double r = lane + off < 32 ? b->scratch[w][lane + off] : v;
+    T r = v;
+    if (src >= 0 && src < 32) std::memcpy(&r, &b->scratch[w][src], sizeof(T));
     pthread_barrier_wait(&b->warp[w]);
     return r;
 }
+}  // namespace cuda_on_host
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) { return cuda_on_host::warp_exchange(v, src & 31); }
+template <typename T>
+static inline T __shfl_down_sync(unsigned, T v, int off) { return cuda_on_host::warp_exchange(v, (int)(threadIdx.x & 31) + off); }
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int off) { return cuda_on_host::warp_exchange(v, (int)(threadIdx.x & 31) - off); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cuda_on_host::block()->warp[threadIdx.x >> 5]); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
@@ -82,7 +96,53 @@ static inline int __float_as_int(float f) {
     std::memcpy(&i, &f, 4);
     return i;
 }
-static inline void __stcs(float* p, float v) { *p = v; }
+template <typename T>
+static inline void __stcs(T* p, T v) { *p = v; }
+template <typename T>
+static inline T __ldcg(const T* p) { return *p; }
+static inline float __int_as_float(int i) {
+    float f;
+    std::memcpy(&f, &i, 4);
+    return f;
+}
+static inline float __uint_as_float(unsigned i) {
+    float f;
+    std::memcpy(&f, &i, 4);
+    return f;
+}
+static inline int __float2int_rd(float f) { return (int)std::floor(f); }
+static inline int __double2int_rz(double d) { return (int)d; }
+static inline float __fmaf_rd(float a, float b, float c) {  // exact product and sum in float64, one rounding down
+    const int mode = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile double t = (double)a * (double)b + (double)c;  // callers keep this exact in float64 (see floor_div8)
+    volatile float r = (float)t;
+    fesetround(mode);
+    return r;
+}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // PRMT, default mode
+    const unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned sel = (s >> (4 * i)) & 0xf;
+        unsigned byte = (unsigned)(src >> (8 * (sel & 7))) & 0xff;
+        if (sel & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline void __nanosleep(unsigned) { sched_yield(); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicInc(unsigned* p, unsigned limit) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST), next;
+    do next = old >= limit ? 0 : old + 1;
+    while (!__atomic_compare_exchange_n(p, &old, next, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return old;
+}
+#define __grid_constant__
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline bool __all_sync(unsigned, bool pred) {
@@ -143,10 +203,8 @@ void launch(dim3 grid, int threads, Kernel kernel) {
 }
 template <typename Kernel>
 void launch_dynamic(dim3 grid, dim3 block, size_t smem_bytes, Kernel kernel) {
-    std::vector<double> buf(smem_bytes / sizeof(double) + 2);  // 16-byte aligned is all a kernel may assume
-    void* p = buf.data();
-    if (reinterpret_cast<uintptr_t>(p) & 15) p = static_cast<char*>(p) + 8;
-    dynamic_smem() = p;
+    std::vector<char> buf(smem_bytes + 256);
+    dynamic_smem() = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf.data()) + 127) & ~(uintptr_t)127);
     launch(grid, (int)block.x, kernel);
     dynamic_smem() = nullptr;
 }

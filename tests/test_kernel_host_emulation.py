@@ -2,7 +2,8 @@
 lk_tile_kernel (every window; frames, gradients, in-tile warp), iter_finalize_kernel, warp_rows_kernel<double> /
 <float> (warp_image of the split refinement iteration), pyramid.cu / pyramid_march.cu with their launchers
 (gradients, both Gaussian-pyramid kernels, warp_kernel, both upsample kernels), and motion.cu, lk_fixed.cu, metrics.cu
-(the fixture generators' warps, the RTL's integer datapath, the verifier's metrics).
+(the fixture generators' warps, the RTL's integer datapath, the verifier's metrics), and lk_march.cu -- the fast marching
+kernels with their TMA ring, mbarriers, packed pairs and warp shuffles (stand-ins in tests/host_emul/emul_lk_march.cpp).
 
 tests/host_emul/emul_*.cpp #include optical-flow-fpga_b200/csrc/lk_tile5.cu / lk_tile.cu / warp_rows.cuh and compile them with
 g++ on top of tests/host_emul/cuda_on_host.h (every CUDA thread of a block is an OS thread, __syncthreads() a barrier,
@@ -489,3 +490,120 @@ def test_metrics_kernels_source_on_cpu(tmp_path_factory):
         want = fmo.all_metrics(u[b], v[b], float(truth[b, 0]), float(truth[b, 1]), mask)
         for k, name in enumerate(("mae_u", "mae_v", "rmse", "epe", "aae")):
             assert out[b, k] == pytest.approx(want[name], rel=2e-6, abs=1e-7), (b, name)
+
+
+# ---------------------------------------------------------------------------------------
+# lk_march.cu: the fast marching kernels (single scale float / uint8 / fixed point, refinement iteration)
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul_march(tmp_path_factory):
+    lib = _build(tmp_path_factory, "emul_lk_march")
+    lib.emul_lk_march.argtypes = [_vp] * 4 + [_i] * 4
+    lib.emul_lk_march_u8.argtypes = [_vp] * 4 + [_i] * 3
+    lib.emul_lk_march_fx.argtypes = [_vp] * 4 + [_i] * 4
+    lib.emul_lk_refine.argtypes = [_i] + [_vp] * 6 + [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 9
+    lib.emul_lk_refine_units_per_pair.argtypes = [_i, _i, _i]
+    return lib
+
+
+TMA_OR_ERROR, PLAIN_LOADS = 1, 2
+
+
+@pytest.mark.parametrize("shape", [(5, 8), (9, 120), (24, 128), (17, 132), (40, 248), (31, 364)])
+def test_marching_kernel_source_on_cpu_uint8_valued_frames(emul_march, shape):
+    """Fast mode is bit-identical to the reference on uint8-valued frames (every partial sum is exact, so the
+    separable association does not matter): both load paths -- the TMA ring (tensor-map boxes with zero fill, row-by-row
+    edge chunks, patched border columns) and plain global loads -- on widths that end inside a strip, one warp wide,
+    several strips wide, heights that are not a multiple of the 8-row chunk."""
+    h, w = shape
+    rng = np.random.default_rng(h * w)
+    p = rng.integers(0, 256, (2, h, w)).astype(f32)
+    c = rng.integers(0, 256, (2, h, w)).astype(f32)
+    want = [orc.lucas_kanade_single_scale(p[b], c[b], 5) for b in range(2)]
+    for path in (TMA_OR_ERROR, PLAIN_LOADS):
+        u, v = np.full_like(p, np.nan), np.full_like(p, np.nan)
+        assert emul_march.emul_lk_march(ptr(p), ptr(c), ptr(u), ptr(v), 2, h, w, path) == 0
+        for b in range(2):
+            assert np.array_equal(bits(u[b]), bits(want[b][0])) and np.array_equal(bits(v[b]), bits(want[b][1])), (path, b)
+
+
+@pytest.mark.parametrize("shape", [(24, 128), (33, 256), (20, 144)])
+def test_marching_kernel_uint8_ingest_and_fixed_point_flavours(emul_march, shape):
+    h, w = shape
+    rng = np.random.default_rng(h + w)
+    p8 = rng.integers(0, 256, (2, h, w)).astype(np.uint8)
+    c8 = rng.integers(0, 256, (2, h, w)).astype(np.uint8)
+    u, v = np.full((2, h, w), np.nan, f32), np.full((2, h, w), np.nan, f32)
+    assert emul_march.emul_lk_march_u8(ptr(p8), ptr(c8), ptr(u), ptr(v), 2, h, w) == 0
+    for b in range(2):
+        uo, vo = orc.lucas_kanade_single_scale(p8[b].astype(f32), c8[b].astype(f32), 5)
+        assert np.array_equal(bits(u[b]), bits(uo)) and np.array_equal(bits(v[b]), bits(vo))
+    for quirk in (1, 0):
+        u16, v16 = np.full((2, h, w), 77, np.int16), np.full((2, h, w), 77, np.int16)
+        assert emul_march.emul_lk_march_fx(ptr(p8), ptr(c8), ptr(u16), ptr(v16), 2, h, w, quirk) == 0
+        for b in range(2):
+            uo, vo = fxo.lk_single_scale_fx(p8[b], c8[b], mirror_avg_quirk=bool(quirk))
+            assert np.array_equal(u16[b], uo) and np.array_equal(v16[b], vo), (quirk, b)
+
+
+def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state=None, rows=None):
+    b, h, w = prev.shape
+    out_u, out_v = np.full_like(fu, 9.0), np.full_like(fv, 9.0)
+    sel = np.zeros(b, np.int32) if state is None else state["sel"]
+    done = np.zeros(b, np.int32) if state is None else state["done"]
+    executed = np.zeros(b, np.int32) if state is None else state["executed"]
+    resid = np.zeros((b, 4, 2), f32) if state is None else state["resid"]
+    lo, hi = rows if rows else (0, h)
+    units = lib.emul_lk_refine_units_per_pair(b, hi - lo, w)  # the kernels index partial[pair][unit][2]
+    partial = np.zeros((b, units, 2))
+    warped = np.zeros_like(prev)
+    cnt = np.zeros(b, np.uint32)
+    rc = lib.emul_lk_refine(form, ptr(prev), ptr(curr), ptr(fu), ptr(fv), ptr(out_u), ptr(out_v), ptr(sel), 0, ptr(done),
+                            ptr(partial), ptr(warped), ptr(cnt), ptr(executed), ptr(resid), 4, iteration, b, h, w, lo, hi, lo, hi)
+    assert rc == 0
+    return out_u, out_v, partial, dict(sel=sel, done=done, executed=executed, resid=resid)
+
+
+def test_fast_refinement_iteration_source_on_cpu(emul_march):
+    """One fast-mode iteration in its three forms.  Split and fused give the same bits; against the reference the
+    iteration is tolerance-level (float32 warp fraction, separable window sums), so the comparison is statistical:
+    flow_out - flow_in equals the oracle's increment except where the 2 x 2 system is ill-conditioned."""
+    from scipy.ndimage import gaussian_filter, shift
+
+    rng = np.random.default_rng(14)
+    b, h, w = 2, 40, 248
+    prev = gaussian_filter((rng.random((b, h, w)) * 255).astype(f32), (0, 1.5, 1.5)).astype(f32)
+    curr = np.stack([shift(prev[0], (0.4, -0.7), order=1, mode="nearest"), shift(prev[1], (-0.6, 0.3), order=1, mode="nearest")]).astype(f32)
+    fu = (rng.standard_normal((b, h, w)) * 0.2).astype(f32)
+    fv = (rng.standard_normal((b, h, w)) * 0.2).astype(f32)
+    split_u, split_v, split_part, _ = _refine_once(emul_march, 0, prev, curr, fu, fv)
+    fused_u, fused_v, fused_part, _ = _refine_once(emul_march, 2, prev, curr, fu, fv)
+    assert np.array_equal(bits(split_u), bits(fused_u)) and np.array_equal(bits(split_v), bits(fused_v))
+    # the sums of |du|, |dv| are formed differently (four float32 magnitudes are added before widening in one form)
+    assert split_part.sum(axis=1) == pytest.approx(fused_part.sum(axis=1), rel=1e-8)
+    for k in range(b):
+        du, dv = orc.lucas_kanade_single_scale(prev[k], orc.warp_image(curr[k], fu[k], fv[k]), 5)
+        err = np.maximum(np.abs(split_u[k] - (fu[k] + du)), np.abs(split_v[k] - (fv[k] + dv)))
+        assert np.median(err) < 1e-5 and (err > 1e-3).mean() < 0.02
+        assert split_part[k, :, 0].sum() == pytest.approx(np.abs(du).astype(np.float64).sum(), rel=1e-3)
+    # rows [row_lo, row_hi) only (row-band mode): the same bits on those rows, nothing written outside
+    band_u, band_v, _, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, rows=(8, 30))
+    assert np.array_equal(bits(band_u[:, 8:30]), bits(split_u[:, 8:30])) and np.array_equal(bits(band_v[:, 8:30]), bits(split_v[:, 8:30]))
+    assert (band_u[:, :8] == 9.0).all() and (band_u[:, 30:] == 9.0).all()
+
+
+def test_fast_refinement_fused_tail_source_on_cpu(emul_march):
+    """form 1: the pair's last warp reduces the partial sums, applies the reference's early-exit test
+    (mean|du| < 0.01 and mean|dv| < 0.01, lucas_kanade_pyramidal.py:213-223) and flips the ping-pong selector."""
+    rng = np.random.default_rng(15)
+    b, h, w = 2, 24, 128
+    prev = (rng.integers(0, 256, (b, h, w))).astype(f32)
+    curr = prev.copy()
+    curr[0] = rng.integers(0, 256, (h, w))  # pair 0 moves, pair 1 does not: its increment is exactly 0
+    zeros = np.zeros_like(prev)
+    out_u, out_v, _, st = _refine_once(emul_march, 1, prev, curr, zeros, zeros.copy())
+    assert st["sel"].tolist() == [1, 1] and st["done"].tolist() == [0, 1] and st["executed"].tolist() == [1, 1]
+    du, dv = orc.lucas_kanade_single_scale(prev[0], curr[0], 5)  # flow_in = 0: the warp is the identity
+    assert np.array_equal(bits(out_u[0]), bits(du)) and np.array_equal(bits(out_v[0]), bits(dv))
+    assert st["resid"][0, 0, 0] == pytest.approx(np.abs(du).mean(), rel=1e-5)
+    assert (out_u[1] == 0).all() and st["resid"][1, 0].tolist() == [0.0, 0.0]
