@@ -387,12 +387,11 @@ __global__ void convergence_update_kernel(const double* __restrict__ sums, int b
     if (mu < OF_CONVERGENCE_EPS && mv < OF_CONVERGENCE_EPS) done[pair] = 1;
 }
 
-#ifndef OF_HOST_EMULATION  // tests/host_emul/ compiles the kernels above with g++ and launches them itself
 cudaError_t launch_convergence_update(const double* sums, int batch, double n_pixels, int* sel, int* done,
                                       int* iters_executed, float* residuals, int max_iters, int iteration,
                                       int* launches, cudaStream_t stream) {
     if (launches) *launches += 1;
-    convergence_update_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(sums, batch, n_pixels, sel, done, iters_executed,
+    OF_LAUNCH(convergence_update_kernel, (batch + 127) / 128, 128, 0, stream, sums, batch, n_pixels, sel, done, iters_executed,
                                                                        residuals, max_iters, iteration);
     return cudaGetLastError();
 }
@@ -400,7 +399,7 @@ cudaError_t launch_convergence_update(const double* sums, int batch, double n_pi
 cudaError_t launch_sum_partials(const double* partial, int blocks_per_pair, double* sums, int batch, int* launches,
                                 cudaStream_t stream) {
     if (launches) *launches += 1;
-    sum_partials_kernel<<<batch, 256, 0, stream>>>(partial, blocks_per_pair, sums);
+    OF_LAUNCH(sum_partials_kernel, batch, 256, 0, stream, partial, blocks_per_pair, sums);
     return cudaGetLastError();
 }
 
@@ -413,7 +412,7 @@ static cudaError_t launch_one(const TileArgs& a, int batch, cudaStream_t stream)
     const int rows = (SRC == SRC_WARP || SRC == SRC_WARPED) ? a.row_hi - a.row_lo : a.H;
     if (rows <= 0) return cudaErrorInvalidValue;
     dim3 grid((a.W + TX - 1) / TX, (rows + TY - 1) / TY, batch);
-    lk_tile_kernel<SRC, WIN><<<grid, TILE_THREADS, smem, stream>>>(a);
+    OF_LAUNCH((lk_tile_kernel<SRC, WIN>), grid, TILE_THREADS, smem, stream, a);
     return cudaGetLastError();
 }
 
@@ -460,9 +459,8 @@ cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, in
 
 cudaError_t launch_iter_finalize(const IterFinalizeArgs& a, int batch, int* launches, cudaStream_t stream) {
     if (launches) *launches += 1;
-    iter_finalize_kernel<<<batch, 256, 0, stream>>>(a);
+    OF_LAUNCH(iter_finalize_kernel, batch, 256, 0, stream, a);
     return cudaGetLastError();
 }
-#endif  // OF_HOST_EMULATION
 
 }  // namespace ofb

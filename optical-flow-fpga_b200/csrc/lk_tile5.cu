@@ -258,7 +258,6 @@ __global__ void __launch_bounds__(T5_THREADS, 3) lk_tile5_kernel(TileArgs a) {
 
 }  // namespace
 
-#ifndef OF_HOST_EMULATION  // tests/host_emul/ compiles the kernel above with g++ and launches it itself
 // same tile geometry as lk_tile.cu (16 x 64), so lk_tile_blocks_per_pair sizes the partial sums for both
 cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t stream) {
     if (batch < 1 || batch > 65535 || (size_t)a.H * a.W >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
@@ -266,12 +265,11 @@ cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t 
     if (rows <= 0) return cudaErrorInvalidValue;
     dim3 grid((a.W + T5_TX - 1) / T5_TX, (rows + T5_TY - 1) / T5_TY, batch);
     switch (src) {
-        case SRC_FRAMES: lk_tile5_kernel<SRC_FRAMES><<<grid, T5_THREADS, 0, stream>>>(a); break;
-        case SRC_WARPED: lk_tile5_kernel<SRC_WARPED><<<grid, T5_THREADS, 0, stream>>>(a); break;
+        case SRC_FRAMES: OF_LAUNCH(lk_tile5_kernel<SRC_FRAMES>, grid, T5_THREADS, 0, stream, a); break;
+        case SRC_WARPED: OF_LAUNCH(lk_tile5_kernel<SRC_WARPED>, grid, T5_THREADS, 0, stream, a); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
-#endif  // OF_HOST_EMULATION
 
 }  // namespace ofb

@@ -152,13 +152,13 @@ cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const f
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (launches) *launches += 1;
-    push_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+    OF_LAUNCH(push_rows_kernel, (unsigned)blocks, 256, 0, stream, a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_t stream) {
     if (launches) *launches += 1;
-    peer_bump_run_kernel<<<1, 1, 0, stream>>>(const_cast<unsigned long long*>(pv.run_id));
+    OF_LAUNCH(peer_bump_run_kernel, 1, 1, 0, stream, const_cast<unsigned long long*>(pv.run_id));
     return cudaGetLastError();
 }
 
@@ -166,7 +166,7 @@ cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long op, int* lau
     PeerSync s;
     fill_peer_sync(s, pv, op);
     if (launches) *launches += 1;
-    peer_sync_kernel<<<1, 32, 0, stream>>>(s);
+    OF_LAUNCH(peer_sync_kernel, 1, 32, 0, stream, s);
     return cudaGetLastError();
 }
 
@@ -188,7 +188,7 @@ cudaError_t launch_peer_allreduce_update(const PeerView& pv, unsigned long long 
     a.partial = partial;
     a.blocks = blocks;
     if (launches) *launches += 1;
-    peer_allreduce_update_kernel<<<1, 256, 0, stream>>>(a);
+    OF_LAUNCH(peer_allreduce_update_kernel, 1, 256, 0, stream, a);
     return cudaGetLastError();
 }
 

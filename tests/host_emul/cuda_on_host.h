@@ -47,7 +47,9 @@ inline void*& dynamic_smem() {
 // launchers written with OF_LAUNCH (of_common.cuh) run unchanged: grid / block / dynamic shared memory as given
 #define OF_LAUNCH(kernel, grid, block, smem, stream, ...) \
     cuda_on_host::launch_dynamic(grid, block, smem, [&]() { kernel(__VA_ARGS__); })
+#ifndef CUDA_ON_HOST_FAKE_RUNTIME  // the whole-library build links tests/host_emul/fake_cudart.cpp instead
 #define cudaGetLastError() cudaSuccess
+#endif
 
 static thread_local uint3 threadIdx;
 static thread_local uint3 blockIdx;
