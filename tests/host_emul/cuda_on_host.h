@@ -32,13 +32,15 @@ struct Block {
     pthread_barrier_t warp[MAX_THREADS / 32];
     double scratch[MAX_THREADS / 32][32];
 };
+// Per OS thread: the launching thread sets both, every worker thread of the launch copies them, so several host
+// threads (the ranks of a row-band run) can have kernels in flight at the same time.
 inline Block*& block() {
-    static Block* b = nullptr;
+    static thread_local Block* b = nullptr;
     return b;
 }
 // dynamic shared memory of the kernel being emulated (set by the harness before launch)
 inline void*& dynamic_smem() {
-    static void* p = nullptr;
+    static thread_local void* p = nullptr;
     return p;
 }
 }  // namespace cuda_on_host
@@ -173,11 +175,15 @@ void launch(dim3 grid, int threads, Kernel kernel) {
         int tid, threads;
         dim3 grid;
         Kernel* k;
+        Block* blk;
+        void* smem;
     };
     std::vector<Arg> args(threads);
     std::vector<pthread_t> tids(threads);
     auto body = [](void* p) -> void* {
         Arg* a = static_cast<Arg*>(p);
+        block() = a->blk;
+        dynamic_smem() = a->smem;
         blockDim = dim3(a->threads, 1, 1);
         gridDim = a->grid;
         threadIdx = uint3{(unsigned)a->tid, 0, 0};
@@ -194,7 +200,7 @@ void launch(dim3 grid, int threads, Kernel kernel) {
     pthread_attr_init(&attr);
     pthread_attr_setstacksize(&attr, 256 * 1024);
     for (int t = 0; t < threads; ++t) {
-        args[t] = Arg{t, threads, grid, &kernel};
+        args[t] = Arg{t, threads, grid, &kernel, &blk, dynamic_smem()};
         pthread_create(&tids[t], &attr, body, &args[t]);
     }
     for (int t = 0; t < threads; ++t) pthread_join(tids[t], nullptr);

@@ -58,7 +58,7 @@ def emul(tmp_path_factory):
 
 @pytest.fixture(scope="module")
 def emul_v1(tmp_path_factory):
-    lib = _build(tmp_path_factory, "emul_lk_tile")
+    lib = _build(tmp_path_factory, "emul_lk_tile", "emul_lk_tile5")  # launch_lk_tile dispatches to launch_lk_tile5
     lib.emul_lk_tile.argtypes = [_i, _i] + [_vp] * 5 + [_i] * 3
     lib.emul_lk_tile_refine.argtypes = [_i, _i] + [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
     lib.emul_iter_finalize.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, C.c_long, _i, _i]
