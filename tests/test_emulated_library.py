@@ -121,3 +121,88 @@ def test_product_runs_end_to_end_on_the_emulated_library():
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-4000:])
     assert "emulated library ok" in res.stdout
+
+
+ROWBAND_CHILD = r"""
+import ctypes as C, multiprocessing as mp, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {backend!r})
+import of_b200, synthetic
+
+bits = lambda a: np.ascontiguousarray(a).view(np.uint32)
+
+
+def rank_main(r, world, shape, levels, iters, repl_px, mode, p, c, conn):
+    assert of_b200.lib().cuda_on_host_use_slice(r, world) == 0  # this rank's part of the shared "device memory"
+    cx = of_b200.RowbandContext(r, world, shape[0], shape[1], levels, 5, iters, mode)
+    conn.send(cx.arena_ptr)
+    cx.set_peers(conn.recv())
+    cx.set_replicate_pixels(repl_px)
+    cx.set_timeout_ms(120000)  # OS threads on a few cores: the ranks drift far more than GPUs do
+    out = []
+    for rep in range(2):  # the second run reuses the arenas and the flag sequence numbers
+        u, v = np.full_like(p, np.nan), np.full_like(p, np.nan)
+        cx.run(p.ctypes.data, c.ctypes.data, u.ctypes.data, v.ctypes.data, 0)
+        it_r, _, err = cx.trace(0)
+        out.append((u, v, it_r.tolist(), err))
+    conn.send(out)
+    conn.recv()
+    cx.close()
+
+
+def run(world, shape, levels, iters, repl_px, mode):
+    prev, curr, _ = synthetic.make_pairs_numpy(1, shape[0], shape[1], seed=31)
+    p, c = np.ascontiguousarray(prev[0]), np.ascontiguousarray(np.roll(curr[0], 3, axis=0))
+    u1, v1, (iters_exec, _) = of_b200.lk_pyramidal(p, c, levels, 5, iters, mode=mode, return_trace=True)
+    ctx = mp.get_context("fork")
+    pipes = [ctx.Pipe() for _ in range(world)]
+    procs = [ctx.Process(target=rank_main, args=(r, world, shape, levels, iters, repl_px, mode, p, c, pipes[r][1])) for r in range(world)]
+    for x in procs:
+        x.start()
+    arenas = [pipes[r][0].recv() for r in range(world)]
+    for r in range(world):
+        pipes[r][0].send(arenas)
+    results = [pipes[r][0].recv() for r in range(world)]
+    for r in range(world):
+        pipes[r][0].send("done")
+    for x in procs:
+        x.join()
+    for r, res in enumerate(results):
+        for rep, (u, v, it_r, err) in enumerate(res):
+            what = (world, shape, levels, iters, repl_px, mode, "rank", r, "run", rep)
+            assert err == 0, what
+            assert it_r == np.asarray(iters_exec).reshape(-1).tolist(), what
+            assert np.array_equal(bits(u), bits(u1)) and np.array_equal(bits(v), bits(v1)), what
+
+
+lib = of_b200.lib()
+lib.cuda_on_host_shared_init.argtypes = [C.c_size_t]
+assert lib.cuda_on_host_shared_init(1 << 30) == 0  # before the ranks fork: they inherit the mapping at one address
+for mode in (of_b200.MODE_EXACT, of_b200.MODE_FAST):
+    run(2, (96, 128), 1, 1, 0, mode)            # one level, split in two
+    run(3, (96, 128), 2, 2, 0, mode)            # every level in row bands
+    run(4, (120, 248), 3, 2, 2000, mode)        # the coarsest level whole on every rank
+print("row bands ok")
+"""
+
+
+def test_row_band_driver_with_ranks_as_processes():
+    """of_rowband_run on 2, 3 and 4 ranks: each rank is a forked process, "peer-mapped device memory" is one shared
+    mapping the fake runtime allocates the arenas from, so the ranks' kernels meet through the flag words and push rows
+    into each other's arenas as they do over NVLink -- peer.cu's collectives, the fused tail's peer all-reduce, the
+    band / halo bookkeeping of of_rowband.inl.  Every rank's gathered flow must equal the whole-frame driver's, bit for
+    bit, with the same early-exit decisions, on two consecutive runs."""
+    import build_emulated_library
+
+    try:
+        lib = build_emulated_library.build()
+    except RuntimeError as e:
+        if "needs g++" in str(e):
+            pytest.skip(str(e))
+        raise
+    backend = ROOT / "optical-flow-fpga_b200"
+    env = dict(os.environ, OF_B200_LIB_NAME=os.path.relpath(lib, backend))
+    code = ROWBAND_CHILD.format(root=str(ROOT), backend=str(backend))
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=1500)
+    assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-4000:])
+    assert "row bands ok" in res.stdout
