@@ -813,7 +813,16 @@ static int refine_dev_impl(const float* prev, const float* curr, float* flow_in_
         a.row_hi = row_hi;
         a.own_lo = own_lo;
         a.own_hi = own_hi;
-        OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, st));
+        if (exact_refine_split()) {
+            float* warped = reinterpret_cast<float*>(static_cast<char*>(workspace) + refine_partial_bytes(batch, height, width));
+            const int halo = window / 2 + 1;
+            OF_CUDA(launch_warp_rows(ra, warped, row_lo - halo < 0 ? 0 : row_lo - halo,
+                                     row_hi + halo > height ? height : row_hi + halo, true, batch, &cnt.n, st));
+            a.in1 = warped;
+            OF_CUDA(launch_lk_tile(SRC_WARPED, window, a, batch, &cnt.n, st));
+        } else {
+            OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, st));
+        }
         blocks = lk_tile_blocks_per_pair(row_hi - row_lo, width);
     }
     OF_CUDA(launch_sum_partials(partial, blocks, sums, batch, &cnt.n, st));

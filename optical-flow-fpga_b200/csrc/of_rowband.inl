@@ -381,7 +381,16 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
                     t.row_hi = hi;
                     t.own_lo = a;
                     t.own_hi = b;
-                    OF_CUDA(launch_lk_tile(SRC_WARP, c.window, t, 1, &cnt.n, st));
+                    if (exact_refine_split()) {
+                        // warp the rows the band's Sobel / window halo can touch, then the tile kernel on the plane
+                        const int halo = c.window / 2 + 1;
+                        OF_CUDA(launch_warp_rows(ra, F(c.warped_off), lo - halo < 0 ? 0 : lo - halo,
+                                                 hi + halo > h ? h : hi + halo, true, 1, &cnt.n, st));
+                        t.in1 = F(c.warped_off);
+                        OF_CUDA(launch_lk_tile(SRC_WARPED, c.window, t, 1, &cnt.n, st));
+                    } else {
+                        OF_CUDA(launch_lk_tile(SRC_WARP, c.window, t, 1, &cnt.n, st));
+                    }
                     blocks = lk_tile_blocks_per_pair(hi - lo, w);
                 }
             }

@@ -95,6 +95,28 @@ gu, gv = lucas_kanade_pyramidal.upsample_flow(fu[:32, :48], fv[:32, :48], (64, 9
 wu, wv = orc.upsample_flow(fu[:32, :48], fv[:32, :48], (64, 96))
 assert same(gu, wu) and same(gv, wv)
 
+# the refinement iteration as a building block (of_lk_refine_f32_dev, what the Python row-band driver calls):
+# rows [row_lo, row_hi) only, sums of |du|, |dv| over the owned rows
+fu32 = (rng.standard_normal(pp.shape) * 0.5).astype(np.float32)
+fv32 = (rng.standard_normal(pp.shape) * 0.5).astype(np.float32)
+du, dv = orc.lucas_kanade_single_scale(pp, orc.warp_image(cc, fu32, fv32), 5)
+H, W = pp.shape
+ws_bytes = of_b200.lk_refine_workspace_bytes(1, H, W)
+ws = np.zeros(ws_bytes, np.uint8)
+for mode in (of_b200.MODE_EXACT, of_b200.MODE_FAST):
+    ou, ov = np.full_like(pp, 5.0), np.full_like(pp, 5.0)
+    sums = np.zeros(2)
+    lo, hi, own_lo, own_hi = 10, 44, 14, 40
+    of_b200.lk_refine_dev(pp.ctypes.data, cc.ctypes.data, fu32.ctypes.data, fv32.ctypes.data, ou.ctypes.data, ov.ctypes.data,
+                          1, H, W, 5, mode, lo, hi, own_lo, own_hi, sums.ctypes.data, ws.ctypes.data, ws_bytes)
+    assert (ou[:lo] == 5.0).all() and (ou[hi:] == 5.0).all()
+    if mode == of_b200.MODE_EXACT:
+        assert same(ou[lo:hi], (fu32 + du)[lo:hi]) and same(ov[lo:hi], (fv32 + dv)[lo:hi])
+        assert abs(sums[0] - np.abs(du[own_lo:own_hi]).astype(np.float64).sum()) <= 1e-9 * sums[0]
+    else:
+        err = np.maximum(np.abs(ou[lo:hi] - (fu32 + du)[lo:hi]), np.abs(ov[lo:hi] - (fv32 + dv)[lo:hi]))
+        assert np.median(err) < 1e-5
+
 # errors come back as exceptions, not crashes
 for bad in (lambda: of_b200.lk_single_scale(p[0], c[0], 4), lambda: of_b200.lk_pyramidal(pp[:4, :4], cc[:4, :4], 5, 5, 3)):
     try:
