@@ -56,6 +56,16 @@ u, v = of_b200.lk_single_scale(g[0], g[1], 5, mode=of_b200.MODE_FAST)  # width 6
 uo, vo = orc.lucas_kanade_single_scale(g[0], g[1], 5)
 assert same(u, uo) and same(v, vo)
 
+# device entry point with planes that are not 16-byte aligned (base pointer offset by one float): the marching kernel
+# moves 128-bit words, so the driver must route them to the reference-order tile kernel
+h_, w_ = 40, 128
+buf_p, buf_c = np.zeros(h_ * w_ + 1, np.float32), np.zeros(h_ * w_ + 1, np.float32)
+buf_p[1:], buf_c[1:] = p[0].ravel(), c[0].ravel()
+out_u, out_v = np.full(h_ * w_ + 1, np.nan, np.float32), np.full(h_ * w_ + 1, np.nan, np.float32)
+of_b200.lk_single_scale_dev(buf_p.ctypes.data + 4, buf_c.ctypes.data + 4, out_u.ctypes.data + 4, out_v.ctypes.data + 4, 1, h_, w_,
+                            5, of_b200.MODE_FAST)
+assert same(out_u[1:].reshape(h_, w_), want[0][0]) and same(out_v[1:].reshape(h_, w_), want[0][1])
+
 # uint8 ingest and the fixed-point mode
 p8, c8 = p.astype(np.uint8), c.astype(np.uint8)
 u, v = of_b200.lk_single_scale_u8_batch(p8, c8, 5, of_b200.MODE_FAST)
