@@ -66,15 +66,22 @@ def lucas_kanade_pyramidal(
     shapes = [(h, w)]
     for _ in range(1, num_levels):
         shapes.insert(0, (int(shapes[0][0] * 0.5), int(shapes[0][1] * 0.5)))
+    # the same report the reference prints while it runs (lucas_kanade_pyramidal.py:172-222); here the whole
+    # coarse-to-fine loop has already run on the device, so it is printed from the returned trace
+    print("Pyramid levels:")
     for level, (lh, lw) in enumerate(shapes):
-        print(f"\nPyramid level {level}/{num_levels - 1}: {lw}x{lh} pixels")
+        print(f"  Level {level}: {lw}x{lh} pixels")
+    for level, (lh, lw) in enumerate(shapes):
+        print(f"\nProcessing pyramid level {level}/{num_levels - 1}...")
+        if level > 0:
+            print(f"  Upsampled flow to {lw}x{lh}")
         for it in range(int(iters[level])):
             print(
                 f"  Iteration {it + 1}/{num_iterations}: "
                 f"mean residual = ({resid[level, it, 0]:.4f}, {resid[level, it, 1]:.4f})"
             )
-        if 0 < iters[level] < num_iterations:
-            print(f"  Converged after {int(iters[level])} iterations")
+            if it + 1 == int(iters[level]) and resid[level, it, 0] < 0.01 and resid[level, it, 1] < 0.01:
+                print(f"  Converged after {it + 1} iterations")
     if os.environ.get("OF_B200_PYRAMID_PLOTS") == "1":
         visualize_pyramid_level(flow_u, flow_v, num_levels - 1, num_levels)
     return flow_u, flow_v
@@ -165,24 +172,44 @@ def main() -> None:
     out_dir = Path(args.output_dir)
     out_dir.mkdir(parents=True, exist_ok=True)
     frame_prev, frame_curr = _load_pair(Path(args.frame_dir), args.height, args.width)
-    print(f"Loaded frames: {args.width}x{args.height}; levels={args.num_levels}, "
-          f"window={args.window_size}x{args.window_size}, iterations/level={args.num_iterations}")
+    bar = "=" * 60
+    print(bar)
+    print("Pyramidal Lucas-Kanade Optical Flow")
+    print(bar)
+    print(f"Loaded frames: {args.width}x{args.height}")
+    print(f"Pyramid levels: {args.num_levels}")
+    print(f"Window size: {args.window_size}x{args.window_size}")
+    print(f"Iterations per level: {args.num_iterations}")
 
+    print("\n" + bar)
+    print("Running Pyramidal Lucas-Kanade...")
+    print(bar)
     u_pyr, v_pyr = lucas_kanade_pyramidal(
         frame_prev, frame_curr, num_levels=args.num_levels, window_size=args.window_size,
         num_iterations=args.num_iterations,
     )
     region = np.s_[105:135, 55:85]
     u_mean, v_mean = float(np.mean(u_pyr[region])), float(np.mean(v_pyr[region]))
+    print("\n" + bar)
+    print("Pyramidal Results")
+    print(bar)
     print(f"Mean flow in test region: u={u_mean:.3f}, v={v_mean:.3f}")
     print(f"Std dev in test region:   u={np.std(u_pyr[region]):.3f}, v={np.std(v_pyr[region]):.3f}")
+    # printed by the reference whatever the frames are (lucas_kanade_pyramidal.py:430)
+    print("Expected: u=15.0, v=0.0 (from generate_test_frames_natural.py --displacement-x 15)")
     u_pyr.tofile(out_dir / "flow_u_pyramidal.bin")
     v_pyr.tofile(out_dir / "flow_v_pyramidal.bin")
-    print(f"Pyramidal flow fields saved to {out_dir}")
+    print(f"\nPyramidal flow fields saved to {out_dir}")
 
     if args.compare:
+        print("\n" + bar)
+        print("Running Single-Scale for Comparison...")
+        print(bar)
         u_single, v_single = lucas_kanade_single_scale(frame_prev, frame_curr, window_size=args.window_size)
         us, vs = float(np.mean(u_single[region])), float(np.mean(v_single[region]))
+        print("\n" + bar)
+        print("Comparison")
+        print(bar)
         print(f"Single-scale: u={us:.3f}, v={vs:.3f}")
         print(f"Pyramidal:    u={u_mean:.3f}, v={v_mean:.3f}")
         print(f"Difference:   u={abs(u_mean - us):.3f}, v={abs(v_mean - vs):.3f}")
@@ -190,6 +217,10 @@ def main() -> None:
             visualize_flow_comparison(u_single, v_single, u_pyr, v_pyr, out_dir / "flow_comparison.png")
         except ImportError:
             print("Matplotlib not available, skipping visualization")
+
+    print("\n" + bar)
+    print("Complete!")
+    print(bar)
 
 
 if __name__ == "__main__":

@@ -90,3 +90,54 @@ def test_reference_verifier_runs_unchanged_on_the_backend_and_reproduces_its_bas
             assert value == want_leaves[path], (path, value, want_leaves[path])
             compared += 1
     assert compared >= 13 * 2 * 5  # five metrics, two methods, thirteen patterns
+
+
+def test_reference_cli_and_drop_in_cli_write_the_same_files(tmp_path):
+    """scripts/regenerate_flow_plots.sh's first step: `python lucas_kanade_reference.py` -- the reference's file and this
+    repository's file of the same name on the same frames must print the same report and write byte-identical
+    flow_u.bin, flow_v.bin and flow_field_python.txt (the file scripts/visualize_flow.py consumes)."""
+    import build_emulated_library
+
+    try:
+        lib = build_emulated_library.build()
+    except RuntimeError as e:
+        if "needs g++" in str(e):
+            pytest.skip(str(e))
+        raise
+    backend = ROOT / "optical-flow-fpga_b200"
+    suite, stubs = tmp_path / "suite", tmp_path / "stubs"
+    (stubs / "matplotlib").mkdir(parents=True)
+    (stubs / "matplotlib" / "__init__.py").write_text(MATPLOTLIB_STUB)
+    res = subprocess.run([sys.executable, str(REF / "generate_test_suite.py"), "--output-dir", str(suite)], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    logs = {}
+    for who, script, path in (("ref", REF / "lucas_kanade_reference.py", [str(REF), str(stubs)]),
+                              ("ours", backend / "lucas_kanade_reference.py", [str(backend), str(stubs)])):
+        out = tmp_path / who
+        env = dict(os.environ, OF_B200_LIB_NAME=os.path.relpath(lib, backend), PYTHONPATH=os.pathsep.join(path))
+        run = subprocess.run([sys.executable, str(script), "--frame-dir", str(suite / "rotate_small"), "--output-dir", str(out)],
+                             cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0, (who, run.stderr[-2000:])
+        logs[who] = run.stdout.replace(str(out), "OUT")
+    assert logs["ours"] == logs["ref"]
+    for name in ("flow_u.bin", "flow_v.bin", "flow_field_python.txt"):
+        assert (tmp_path / "ours" / name).read_bytes() == (tmp_path / "ref" / name).read_bytes(), name
+
+    # the second step of the script: `python lucas_kanade_pyramidal.py` -- the per-level / per-iteration report and the
+    # saved flow fields, on a moving pattern and on one that converges in its first iteration
+    for pattern in ("translate_medium", "no_motion"):
+        logs = {}
+        for who, script, path in (("ref", REF / "lucas_kanade_pyramidal.py", [str(REF), str(stubs)]),
+                                  ("ours", backend / "lucas_kanade_pyramidal.py", [str(backend), str(stubs)])):
+            out = tmp_path / f"{who}_{pattern}"
+            out.mkdir()
+            env = dict(os.environ, OF_B200_LIB_NAME=os.path.relpath(lib, backend), PYTHONPATH=os.pathsep.join(path))
+            run = subprocess.run([sys.executable, str(script), "--frame-dir", str(suite / pattern), "--output-dir", str(out / "o")],
+                                 cwd=out, env=env, capture_output=True, text=True, timeout=900)
+            assert run.returncode == 0, (who, pattern, run.stderr[-2000:])
+            logs[who] = [ln for ln in run.stdout.replace(str(out), "OUT").splitlines() if "visualization saved" not in ln]
+        assert logs["ours"] == logs["ref"], pattern
+        for name in ("flow_u_pyramidal.bin", "flow_v_pyramidal.bin"):
+            a = (tmp_path / f"ours_{pattern}" / "o" / name).read_bytes()
+            assert a == (tmp_path / f"ref_{pattern}" / "o" / name).read_bytes(), (pattern, name)
