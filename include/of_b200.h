@@ -35,7 +35,8 @@ typedef enum of_status {
     OF_ERR_CUDA = 2,
     OF_ERR_UNSUPPORTED = 3,
     OF_ERR_NO_DEVICE = 4,
-    OF_ERR_OUT_OF_MEMORY = 5
+    OF_ERR_OUT_OF_MEMORY = 5,
+    OF_ERR_PEER_TIMEOUT = 6 /* row-band mode: a peer rank did not answer in time; the run's flow is invalid */
 } of_status;
 
 /* Arithmetic mode of the float path.
@@ -62,6 +63,11 @@ int of_set_device(int ordinal);
 long long of_kernel_launches(void);     /* kernels launched by this library so far      */
 int of_host_alloc_pinned(void** ptr, size_t bytes);
 int of_host_free_pinned(void* ptr);
+/* The host-buffer entry points keep grow-only device buffers and three streams PER DEVICE ORDINAL (the
+ * device current at the call), so one process -- or several threads, each with its own current device --
+ * can drive several GPUs.  of_release_host_buffers frees the current device's buffers (they are
+ * re-allocated on demand); host calls on one device are serialised, calls on different devices are not. */
+int of_release_host_buffers(void);
 
 /* ---- host-buffer entry points ------------------------------------------------------- */
 
@@ -266,8 +272,13 @@ int of_rowband_set_timeout_ms(of_rowband_t* ctx, int milliseconds);
 int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, float* u, float* v, void* stream);
 int of_rowband_result(const of_rowband_t* ctx, const float** u, const float** v);
 /* waits for `stream`, then copies out (each optional) iters_executed[levels] (level 0 = coarsest),
- * residuals[levels][iterations][2] and the error word (non-zero: a peer did not answer in time) */
+ * residuals[levels][iterations][2] and the error word (non-zero: a peer did not answer in time).
+ * Returns OF_ERR_PEER_TIMEOUT when the error word is set: the flow of that run is garbage.  The word stays
+ * set until the host has read it here; the next of_rowband_run after that starts clean (a time-out can be
+ * as harmless as ranks entering a cold first run too far apart). */
 int of_rowband_trace(of_rowband_t* ctx, int* iters_executed, float* residuals, int* error, void* stream);
+/* the same check without the trace: OF_OK, or OF_ERR_PEER_TIMEOUT (call it before trusting of_rowband_result) */
+int of_rowband_status(of_rowband_t* ctx, void* stream);
 int of_rowband_destroy(of_rowband_t* ctx);
 
 #ifdef __cplusplus

@@ -33,26 +33,53 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
 def up_to_date() -> bool:
-    if not LIB.exists():
-        return False
-    t = LIB.stat().st_mtime
     deps = [CSRC / s for s in SOURCES] + [CSRC / h for h in HEADERS] + [Path(__file__)]
-    return all(d.stat().st_mtime <= t for d in deps)
+    return not _stale(LIB, deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and up_to_date():
+    """One object per source (compiled in parallel, rebuilt only when the source or a header changed), then
+    the shared library.  OF_NVCC_DEFS (experiments) changes the flags, so it forces a full rebuild."""
+    if not force and up_to_date() and not os.environ.get("OF_NVCC_DEFS"):
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, *os.environ.get("OF_NVCC_DEFS", "").split()]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = find_nvcc()
+    extra = os.environ.get("OF_NVCC_DEFS", "").split()
+    objdir = HERE / "build" / (LIB.stem + ("_defs" if extra else ""))
+    objdir.mkdir(parents=True, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    headers = [CSRC / h for h in HEADERS] + [Path(__file__)]
+
+    def compile_one(src: str):
+        obj = objdir / (Path(src).stem + ".o")
+        if not (force or extra) and not _stale(obj, [CSRC / src] + headers):
+            return obj, None
+        res = subprocess.run([nvcc, *flags, "-c", "-o", str(obj), str(CSRC / src)], capture_output=True, text=True)
+        return obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = False
+    for _, res in results:
+        if res is not None and (verbose or res.returncode != 0):
+            sys.stderr.write(res.stdout + res.stderr)
+        failed |= res is not None and res.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libof_b200.so")
+    link = [nvcc, "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)]
+    res = subprocess.run(link + [str(o) for o, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libof_b200.so")
     return LIB
 
 

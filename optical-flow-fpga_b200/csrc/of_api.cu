@@ -20,7 +20,6 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-std::mutex g_host_mutex;  // host-buffer entry points share one device arena
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -81,15 +80,70 @@ struct Arena {
         *out = ptr[idx];
         return OF_OK;
     }
+    void release() {
+        for (void* p : ptr)
+            if (p) cudaFree(p);
+        ptr.clear();
+        cap.clear();
+    }
 };
-Arena g_arena;
-cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
 
-int host_streams() {
-    for (int i = 0; i < 3; ++i)
-        if (!g_streams[i]) OF_CUDA(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
+// State of the host-buffer entry points, one per device ordinal: buffers and streams belong to the
+// device that was current when they were created, so a process (or several threads) driving more
+// than one GPU gets one set per GPU.  The mutex serialises the host calls of one device only.
+constexpr int HOST_STREAMS = 3;
+struct HostPath {
+    std::mutex mutex;
+    Arena arena;
+    cudaStream_t streams[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    int device = -1;
+    // every stream drained: called before a host entry point returns, on success and on failure, so no
+    // copy into the caller's or the arena's buffers is in flight once the mutex is released
+    cudaError_t drain() {
+        cudaError_t first = cudaSuccess;
+        for (int i = 0; i < HOST_STREAMS; ++i)
+            if (streams[i]) {
+                const cudaError_t e = cudaStreamSynchronize(streams[i]);
+                if (e != cudaSuccess && first == cudaSuccess) first = e;
+            }
+        return first;
+    }
+};
+constexpr int MAX_DEVICES = 64;
+std::mutex g_host_paths_mutex;
+HostPath* g_host_paths[MAX_DEVICES] = {nullptr};
+
+int host_path(HostPath** out) {
+    int dev = 0;
+    OF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(OF_ERR_UNSUPPORTED, "device ordinal out of range");
+    std::lock_guard<std::mutex> lock(g_host_paths_mutex);
+    if (!g_host_paths[dev]) {
+        g_host_paths[dev] = new HostPath();
+        g_host_paths[dev]->device = dev;
+    }
+    HostPath* hp = g_host_paths[dev];
+    for (int i = 0; i < HOST_STREAMS; ++i)
+        if (!hp->streams[i]) OF_CUDA(cudaStreamCreateWithFlags(&hp->streams[i], cudaStreamNonBlocking));
+    *out = hp;
     return OF_OK;
 }
+
+// Drains the device's host-path streams when a host entry point returns -- on the failure paths too, so
+// no copy into the caller's or the arena's buffers is still in flight once the mutex is released.
+struct HostDrain {
+    HostPath* hp;
+    ~HostDrain() {
+        if (hp->drain() != cudaSuccess) cudaGetLastError();
+    }
+};
+
+// the current device's host-path state, locked for the rest of the calling scope
+#define OF_HOST_PATH(hp)           \
+    HostPath* hp = nullptr;        \
+    OF_TRY(host_path(&hp));        \
+    std::lock_guard<std::mutex> lock(hp->mutex); \
+    HostDrain drain_guard{hp}
 
 int check_frame(const void* a, const void* b, int H, int W) {
     if (!a || !b) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
@@ -407,7 +461,24 @@ long long of_kernel_launches(void) { return g_launches.load(); }
 int of_host_alloc_pinned(void** ptr, size_t bytes) {
     if (!ptr) return fail(OF_ERR_INVALID_ARGUMENT, "null pointer");
     OF_TRY(need_device());
-    OF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    // portable: pinned for every CUDA context of the process (a process that drives several GPUs)
+    OF_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return OF_OK;
+}
+
+int of_release_host_buffers(void) {
+    int dev = 0;
+    OF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return OF_OK;
+    HostPath* hp = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_host_paths_mutex);
+        hp = g_host_paths[dev];
+    }
+    if (!hp) return OF_OK;
+    std::lock_guard<std::mutex> lock(hp->mutex);
+    if (hp->drain() != cudaSuccess) cudaGetLastError();
+    hp->arena.release();
     return OF_OK;
 }
 
@@ -436,8 +507,7 @@ int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float
     if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
     if (batch == 0) return OF_OK;
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t plane = (size_t)height * width;
     // chunks of <= 64 MiB per array, three in flight: H2D of chunk i+1 and D2H of chunk i-1
@@ -455,10 +525,10 @@ int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float
     const int slots = n_chunks < 3 ? n_chunks : 3;
     float* d[3][4];
     for (int s = 0; s < slots; ++s)
-        for (int j = 0; j < 4; ++j) OF_TRY(g_arena.get(s * 4 + j, chunk_bytes, reinterpret_cast<void**>(&d[s][j])));
+        for (int j = 0; j < 4; ++j) OF_TRY(hp->arena.get(s * 4 + j, chunk_bytes, reinterpret_cast<void**>(&d[s][j])));
     for (int c = 0; c < n_chunks; ++c) {
         const int s = c % slots;
-        cudaStream_t st = g_streams[s];
+        cudaStream_t st = hp->streams[s];
         const size_t b0 = (size_t)c * per_chunk;
         const int nb = (int)((size_t)batch - b0 < per_chunk ? (size_t)batch - b0 : per_chunk);
         const size_t bytes = (size_t)nb * plane * sizeof(float);
@@ -468,7 +538,7 @@ int of_lk_single_scale_f32(const float* prev, const float* curr, float* u, float
         OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d[s][2], bytes, cudaMemcpyDeviceToHost, st));
         OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d[s][3], bytes, cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(g_streams[s]));
+    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(hp->streams[s]));
     return OF_OK;
 }
 
@@ -477,13 +547,12 @@ int of_gradients_f32(const float* prev, const float* curr, float* ix, float* iy,
     OF_TRY(check_frame(ix, iy, height, width));
     if (!it) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t bytes = (size_t)height * width * sizeof(float);
     float* d[5];
-    for (int j = 0; j < 5; ++j) OF_TRY(g_arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
-    cudaStream_t st = g_streams[0];
+    for (int j = 0; j < 5; ++j) OF_TRY(hp->arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(d[0], prev, bytes, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[1], curr, bytes, cudaMemcpyHostToDevice, st));
     OF_CUDA(launch_gradients(d[0], d[1], d[2], d[3], d[4], 1, height, width, &cnt.n, st));
@@ -501,13 +570,12 @@ int of_lk_from_gradients_f32(const float* ix, const float* iy, const float* it, 
     if (!it) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
     OF_TRY(check_window(window));
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t bytes = (size_t)height * width * sizeof(float);
     float* d[5];
-    for (int j = 0; j < 5; ++j) OF_TRY(g_arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
-    cudaStream_t st = g_streams[0];
+    for (int j = 0; j < 5; ++j) OF_TRY(hp->arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(d[0], ix, bytes, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[1], iy, bytes, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[2], it, bytes, cudaMemcpyHostToDevice, st));
@@ -534,14 +602,13 @@ int of_pyramid_down_f32(const float* src, float* dst, int height, int width, int
     if (!weights || radius < 0 || radius > OF_MAX_GAUSS_RADIUS)
         return fail(OF_ERR_INVALID_ARGUMENT, "gaussian weights missing or radius out of range");
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t ib = (size_t)height * width * sizeof(float), ob = (size_t)out_height * out_width * sizeof(float);
     float *ds, *dd;
-    OF_TRY(g_arena.get(0, ib, reinterpret_cast<void**>(&ds)));
-    OF_TRY(g_arena.get(1, ob, reinterpret_cast<void**>(&dd)));
-    cudaStream_t st = g_streams[0];
+    OF_TRY(hp->arena.get(0, ib, reinterpret_cast<void**>(&ds)));
+    OF_TRY(hp->arena.get(1, ob, reinterpret_cast<void**>(&dd)));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(ds, src, ib, cudaMemcpyHostToDevice, st));
     OF_CUDA(launch_pyramid_down(ds, dd, 1, height, width, out_height, out_width, weights, radius, 0, out_height, &cnt.n,
                                 st));
@@ -554,13 +621,12 @@ int of_warp_f32(const float* image, const float* flow_u, const float* flow_v, fl
     OF_TRY(check_frame(image, out, height, width));
     OF_TRY(check_frame(flow_u, flow_v, height, width));
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t bytes = (size_t)height * width * sizeof(float);
     float* d[4];
-    for (int j = 0; j < 4; ++j) OF_TRY(g_arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
-    cudaStream_t st = g_streams[0];
+    for (int j = 0; j < 4; ++j) OF_TRY(hp->arena.get(j, bytes, reinterpret_cast<void**>(&d[j])));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(d[0], image, bytes, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[1], flow_u, bytes, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[2], flow_v, bytes, cudaMemcpyHostToDevice, st));
@@ -575,17 +641,16 @@ int of_upsample_flow_f32(const float* coarse_u, const float* coarse_v, float* u,
     OF_TRY(check_frame(coarse_u, coarse_v, coarse_height, coarse_width));
     OF_TRY(check_frame(u, v, target_height, target_width));
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t cb = (size_t)coarse_height * coarse_width * sizeof(float);
     const size_t tb = (size_t)target_height * target_width * sizeof(float);
     float* d[4];
-    OF_TRY(g_arena.get(0, cb, reinterpret_cast<void**>(&d[0])));
-    OF_TRY(g_arena.get(1, cb, reinterpret_cast<void**>(&d[1])));
-    OF_TRY(g_arena.get(2, tb, reinterpret_cast<void**>(&d[2])));
-    OF_TRY(g_arena.get(3, tb, reinterpret_cast<void**>(&d[3])));
-    cudaStream_t st = g_streams[0];
+    OF_TRY(hp->arena.get(0, cb, reinterpret_cast<void**>(&d[0])));
+    OF_TRY(hp->arena.get(1, cb, reinterpret_cast<void**>(&d[1])));
+    OF_TRY(hp->arena.get(2, tb, reinterpret_cast<void**>(&d[2])));
+    OF_TRY(hp->arena.get(3, tb, reinterpret_cast<void**>(&d[3])));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(d[0], coarse_u, cb, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(d[1], coarse_v, cb, cudaMemcpyHostToDevice, st));
     OF_CUDA(launch_upsample_flow(d[0], d[1], nullptr, nullptr, nullptr, 0, d[2], d[3], 1, coarse_height, coarse_width,
@@ -629,48 +694,58 @@ int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v
     if (iterations < 0) return fail(OF_ERR_INVALID_ARGUMENT, "num_iterations must be >= 0");
     if (batch == 0) return OF_OK;
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t plane = (size_t)height * width;
-    // pairs per pass: keep frames + workspace of one pass around 2 GiB
-    size_t per_pass = (size_t)(256u << 20) / (plane * sizeof(float));
+    // Passes of a few pairs each, three in flight on three streams with their own frames, workspace and trace
+    // buffers: H2D of pass i+1 and D2H of pass i-1 overlap the kernels of pass i (pinned host memory needed
+    // for the copies to actually overlap).  A pass holds at most 128 MiB per frame stack, and a batch is cut
+    // into at least six passes when it has that many pairs, so that the pipeline has something to overlap.
+    size_t per_pass = ((size_t)128 << 20) / (plane * sizeof(float));
     if (per_pass < 1) per_pass = 1;
-    if (per_pass > (size_t)batch) per_pass = batch;
+    const size_t sixth = ((size_t)batch + 5) / 6;
+    if (per_pass > sixth) per_pass = sixth;
     if (per_pass > 65535) per_pass = 65535;
+    const int n_pass = (int)(((size_t)batch + per_pass - 1) / per_pass);
+    const int slots = n_pass < HOST_STREAMS ? n_pass : HOST_STREAMS;
     PyrPlan plan;
     OF_TRY(make_plan((int)per_pass, height, width, levels, plan));
     const size_t fb = per_pass * plane * sizeof(float);
-    float* d[4];
-    for (int j = 0; j < 4; ++j) OF_TRY(g_arena.get(j, fb, reinterpret_cast<void**>(&d[j])));
-    void* ws;
-    OF_TRY(g_arena.get(4, plan.total, &ws));
-    int* d_iters = nullptr;
-    float* d_res = nullptr;
     const size_t ib = per_pass * levels * sizeof(int);
     const size_t rb = per_pass * levels * (size_t)(iterations > 0 ? iterations : 1) * 2 * sizeof(float);
-    if (iters_executed) OF_TRY(g_arena.get(5, ib, reinterpret_cast<void**>(&d_iters)));
-    if (residuals) OF_TRY(g_arena.get(6, rb, reinterpret_cast<void**>(&d_res)));
-    cudaStream_t st = g_streams[0];
-    for (size_t b0 = 0; b0 < (size_t)batch; b0 += per_pass) {
+    float* d[HOST_STREAMS][4];
+    void* ws[HOST_STREAMS];
+    int* d_iters[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    float* d_res[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    for (int s = 0; s < slots; ++s) {
+        const size_t base = 32 + (size_t)s * 8;
+        for (int j = 0; j < 4; ++j) OF_TRY(hp->arena.get(base + j, fb, reinterpret_cast<void**>(&d[s][j])));
+        OF_TRY(hp->arena.get(base + 4, plan.total, &ws[s]));
+        if (iters_executed) OF_TRY(hp->arena.get(base + 5, ib, reinterpret_cast<void**>(&d_iters[s])));
+        if (residuals) OF_TRY(hp->arena.get(base + 6, rb, reinterpret_cast<void**>(&d_res[s])));
+    }
+    for (int c = 0; c < n_pass; ++c) {
+        const int s = c % slots;
+        cudaStream_t st = hp->streams[s];
+        const size_t b0 = (size_t)c * per_pass;
         const int nb = (int)((size_t)batch - b0 < per_pass ? (size_t)batch - b0 : per_pass);
         const size_t bytes = (size_t)nb * plane * sizeof(float);
-        OF_CUDA(cudaMemcpyAsync(d[0], prev + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
-        OF_CUDA(cudaMemcpyAsync(d[1], curr + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
+        OF_CUDA(cudaMemcpyAsync(d[s][0], prev + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
+        OF_CUDA(cudaMemcpyAsync(d[s][1], curr + b0 * plane, bytes, cudaMemcpyHostToDevice, st));
         PyrPlan pp;
         OF_TRY(make_plan(nb, height, width, levels, pp));
-        OF_TRY(pyramidal_dev(d[0], d[1], d[2], d[3], nb, height, width, levels, window, iterations, mode,
-                             gauss_weights, gauss_radius, ws, pp.total, d_iters, d_res, st, cnt));
-        OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d[2], bytes, cudaMemcpyDeviceToHost, st));
-        OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d[3], bytes, cudaMemcpyDeviceToHost, st));
+        OF_TRY(pyramidal_dev(d[s][0], d[s][1], d[s][2], d[s][3], nb, height, width, levels, window, iterations, mode,
+                             gauss_weights, gauss_radius, ws[s], pp.total, d_iters[s], d_res[s], st, cnt));
+        OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d[s][2], bytes, cudaMemcpyDeviceToHost, st));
+        OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d[s][3], bytes, cudaMemcpyDeviceToHost, st));
         if (iters_executed)
-            OF_CUDA(cudaMemcpyAsync(iters_executed + b0 * levels, d_iters, (size_t)nb * levels * sizeof(int),
+            OF_CUDA(cudaMemcpyAsync(iters_executed + b0 * levels, d_iters[s], (size_t)nb * levels * sizeof(int),
                                     cudaMemcpyDeviceToHost, st));
         if (residuals && iterations > 0)
-            OF_CUDA(cudaMemcpyAsync(residuals + b0 * levels * iterations * 2, d_res,
+            OF_CUDA(cudaMemcpyAsync(residuals + b0 * levels * iterations * 2, d_res[s],
                                     (size_t)nb * levels * iterations * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        OF_CUDA(cudaStreamSynchronize(st));
     }
+    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(hp->streams[s]));
     return OF_OK;
 }
 
@@ -863,16 +938,15 @@ int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, 
     if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
     if (batch == 0) return OF_OK;
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     const size_t n = (size_t)batch * height * width;
     uint8_t *dp, *dc;
     int16_t *du, *dv;
-    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&dp)));
-    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dc)));
-    OF_TRY(g_arena.get(2, n * 2, reinterpret_cast<void**>(&du)));
-    OF_TRY(g_arena.get(3, n * 2, reinterpret_cast<void**>(&dv)));
-    cudaStream_t st = g_streams[0];
+    OF_TRY(hp->arena.get(0, n, reinterpret_cast<void**>(&dp)));
+    OF_TRY(hp->arena.get(1, n, reinterpret_cast<void**>(&dc)));
+    OF_TRY(hp->arena.get(2, n * 2, reinterpret_cast<void**>(&du)));
+    OF_TRY(hp->arena.get(3, n * 2, reinterpret_cast<void**>(&dv)));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(dp, prev, n, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(dc, curr, n, cudaMemcpyHostToDevice, st));
     OF_TRY(of_lk_single_scale_fx_dev(dp, dc, du, dv, batch, height, width, flags, st));
@@ -909,8 +983,7 @@ int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, fl
     if (batch < 0) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be >= 0");
     if (batch == 0) return OF_OK;
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     Counter cnt;
     const size_t plane = (size_t)height * width;
     size_t per_chunk = ((size_t)64 << 20) / (plane * sizeof(float));
@@ -922,13 +995,13 @@ int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, fl
     uint8_t* d8[3][2];
     float* df[3][4];
     for (int s = 0; s < slots; ++s) {
-        for (int j = 0; j < 2; ++j) OF_TRY(g_arena.get(12 + s * 2 + j, per_chunk * plane, reinterpret_cast<void**>(&d8[s][j])));
+        for (int j = 0; j < 2; ++j) OF_TRY(hp->arena.get(12 + s * 2 + j, per_chunk * plane, reinterpret_cast<void**>(&d8[s][j])));
         for (int j = 0; j < 2; ++j)
-            OF_TRY(g_arena.get(s * 4 + 2 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][2 + j])));
+            OF_TRY(hp->arena.get(s * 4 + 2 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][2 + j])));
     }
     for (int c = 0; c < n_chunks; ++c) {
         const int s = c % slots;
-        cudaStream_t st = g_streams[s];
+        cudaStream_t st = hp->streams[s];
         const size_t b0 = (size_t)c * per_chunk;
         const int nb = (int)((size_t)batch - b0 < per_chunk ? (size_t)batch - b0 : per_chunk);
         OF_CUDA(cudaMemcpyAsync(d8[s][0], prev + b0 * plane, (size_t)nb * plane, cudaMemcpyHostToDevice, st));
@@ -937,7 +1010,7 @@ int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, fl
             OF_CUDA(launch_lk_march_u8(d8[s][0], d8[s][1], df[s][2], df[s][3], nb, height, width, &cnt.n, st));
         } else {
             for (int j = 0; j < 2; ++j) {
-                OF_TRY(g_arena.get(s * 4 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][j])));
+                OF_TRY(hp->arena.get(s * 4 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][j])));
                 OF_CUDA(launch_u8_to_f32(d8[s][j], df[s][j], (size_t)nb * plane, &cnt.n, st));
             }
             OF_TRY(single_scale_dev(df[s][0], df[s][1], df[s][2], df[s][3], nb, height, width, window, mode, st, cnt));
@@ -945,7 +1018,7 @@ int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, fl
         OF_CUDA(cudaMemcpyAsync(u + b0 * plane, df[s][2], (size_t)nb * plane * sizeof(float), cudaMemcpyDeviceToHost, st));
         OF_CUDA(cudaMemcpyAsync(v + b0 * plane, df[s][3], (size_t)nb * plane * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(g_streams[s]));
+    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(hp->streams[s]));
     return OF_OK;
 }
 
@@ -1045,15 +1118,14 @@ int of_apply_motion_u8(const uint8_t* frames, uint8_t* out, int batch, int heigh
     if (!dx || !dy) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
     if (batch < 1 || batch > 65535 || height > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch and height must be in 1..65535");
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     const size_t n = (size_t)batch * height * width;
     uint8_t *ds, *dd;
     double* dsh;
-    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&ds)));
-    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dd)));
-    OF_TRY(g_arena.get(2, (size_t)batch * 2 * sizeof(double), reinterpret_cast<void**>(&dsh)));
-    cudaStream_t st = g_streams[0];
+    OF_TRY(hp->arena.get(0, n, reinterpret_cast<void**>(&ds)));
+    OF_TRY(hp->arena.get(1, n, reinterpret_cast<void**>(&dd)));
+    OF_TRY(hp->arena.get(2, (size_t)batch * 2 * sizeof(double), reinterpret_cast<void**>(&dsh)));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(ds, frames, n, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(dsh, dx, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(dsh + batch, dy, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1103,13 +1175,12 @@ int of_warp_affine_u8(const uint8_t* frames, uint8_t* out, int batch, int height
     if (!matrices) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
     if (batch < 1 || batch > 65535 || height > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch and height must be in 1..65535");
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     const size_t n = (size_t)batch * height * width;
     uint8_t *ds, *dd;
-    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&ds)));
-    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dd)));
-    cudaStream_t st = g_streams[0];
+    OF_TRY(hp->arena.get(0, n, reinterpret_cast<void**>(&ds)));
+    OF_TRY(hp->arena.get(1, n, reinterpret_cast<void**>(&dd)));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(ds, frames, n, cudaMemcpyHostToDevice, st));
     OF_TRY(of_warp_affine_u8_dev(ds, dd, batch, height, width, matrices, cval, st));
     OF_CUDA(cudaMemcpyAsync(out, dd, n, cudaMemcpyDeviceToHost, st));
@@ -1145,18 +1216,17 @@ int of_flow_metrics_f32(const float* u, const float* v, const float* u_true, con
     if (!u_true || !v_true || !metrics) return fail(OF_ERR_INVALID_ARGUMENT, "null buffer");
     if (batch < 1 || batch > 65535) return fail(OF_ERR_INVALID_ARGUMENT, "batch must be in 1..65535");
     OF_TRY(need_device());
-    std::lock_guard<std::mutex> lock(g_host_mutex);
-    OF_TRY(host_streams());
+    OF_HOST_PATH(hp);
     const size_t n = (size_t)batch * height * width * sizeof(float);
     const size_t ws = of_flow_metrics_workspace_bytes(batch, height, width);
     float *du, *dv, *dt;
     double *dm, *dw;
-    OF_TRY(g_arena.get(0, n, reinterpret_cast<void**>(&du)));
-    OF_TRY(g_arena.get(1, n, reinterpret_cast<void**>(&dv)));
-    OF_TRY(g_arena.get(2, (size_t)batch * 2 * sizeof(float), reinterpret_cast<void**>(&dt)));
-    OF_TRY(g_arena.get(3, (size_t)batch * 5 * sizeof(double), reinterpret_cast<void**>(&dm)));
-    OF_TRY(g_arena.get(4, ws, reinterpret_cast<void**>(&dw)));
-    cudaStream_t st = g_streams[0];
+    OF_TRY(hp->arena.get(0, n, reinterpret_cast<void**>(&du)));
+    OF_TRY(hp->arena.get(1, n, reinterpret_cast<void**>(&dv)));
+    OF_TRY(hp->arena.get(2, (size_t)batch * 2 * sizeof(float), reinterpret_cast<void**>(&dt)));
+    OF_TRY(hp->arena.get(3, (size_t)batch * 5 * sizeof(double), reinterpret_cast<void**>(&dm)));
+    OF_TRY(hp->arena.get(4, ws, reinterpret_cast<void**>(&dw)));
+    cudaStream_t st = hp->streams[0];
     OF_CUDA(cudaMemcpyAsync(du, u, n, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(dv, v, n, cudaMemcpyHostToDevice, st));
     OF_CUDA(cudaMemcpyAsync(dt, u_true, (size_t)batch * sizeof(float), cudaMemcpyHostToDevice, st));

@@ -223,15 +223,15 @@ struct PeerView {
     char* peer[PEER_MAX_WORLD];  // arena base of every rank as mapped in this process (peer[rank] = own)
     int world, rank;
     size_t flag_off, xchg_off;   // unsigned long long flags[PEER_SLOTS][PEER_MAX_WORLD]; double xchg[PEER_SLOTS][PEER_MAX_WORLD][2]
-    int* err;                    // sticky error word in the local arena (a wait timed out)
+    int* err;                    // error word in the local arena (a wait timed out); sticky until the host has read it
     unsigned long long timeout_ns;
     // sequence number of collective `op` of a run = *run_id * ops_per_run + op (run_id: device word)
     const unsigned long long* run_id;
     unsigned long long ops_per_run;
 };
 void fill_peer_sync(PeerSync& s, const PeerView& pv, unsigned long long op);
-// first kernel of a run: ++*run_id
-cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_t stream);
+// first kernel of a run: ++*run_id; clear_error: also reset the error word (the host has seen it)
+cudaError_t launch_peer_begin_run(const PeerView& pv, bool clear_error, int* launches, cudaStream_t stream);
 // rows of a plane (current ping-pong buffer: sel[0] ^ sel_xor ? src1 : src0) -> byte offset dst_off
 // of every rank's arena; `first` / `count` in elements
 cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,

@@ -43,6 +43,7 @@ struct RowbandCtx {
     // step, short enough that a dead peer does not wedge the device.  Ranks must therefore enter
     // of_rowband_run within this time of each other.
     unsigned long long timeout_ns = 4000000000ULL;
+    bool error_seen = false;  // the host has read a non-zero error word: the next run clears it
 };
 
 void rb_shard(int n, int rank, int world, int* a, int* b) {
@@ -246,7 +247,8 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
     double* partial = reinterpret_cast<double*>(c.base + c.partial_off);
     const int L = c.L, iters = c.iters, world = c.world, rank = c.rank;
     unsigned long long op = 0;  // index of the next collective of this run
-    OF_CUDA(launch_peer_begin_run(pv, &cnt.n, st));
+    OF_CUDA(launch_peer_begin_run(pv, c.error_seen, &cnt.n, st));
+    c.error_seen = false;
 
     // per-run control words (not the flags / exchange slots: their sequence numbers keep growing)
     OF_CUDA(cudaMemsetAsync(c.base + c.sel_off, 0, c.resid_off + align_up(sizeof(float) * L * (iters > 0 ? iters : 1) * 2) - c.sel_off, st));
@@ -452,9 +454,17 @@ int of_rowband_trace(of_rowband_t* ctx, int* iters_executed, float* residuals, i
     if (iters_executed) OF_CUDA(cudaMemcpy(iters_executed, c.base + c.itx_off, sizeof(int) * c.L, cudaMemcpyDeviceToHost));
     if (residuals && c.iters > 0)
         OF_CUDA(cudaMemcpy(residuals, c.base + c.resid_off, sizeof(float) * c.L * c.iters * 2, cudaMemcpyDeviceToHost));
-    if (error) OF_CUDA(cudaMemcpy(error, c.base + c.err_off, sizeof(int), cudaMemcpyDeviceToHost));
+    int err = 0;
+    OF_CUDA(cudaMemcpy(&err, c.base + c.err_off, sizeof(int), cudaMemcpyDeviceToHost));
+    if (error) *error = err;
+    if (err != 0) {
+        c.error_seen = true;  // reported: the next of_rowband_run starts with a clean error word
+        return fail(OF_ERR_PEER_TIMEOUT, "row-band run: a peer rank did not answer within the time-out; the flow of this run is invalid");
+    }
     return OF_OK;
 }
+
+int of_rowband_status(of_rowband_t* ctx, void* stream) { return of_rowband_trace(ctx, nullptr, nullptr, nullptr, stream); }
 
 int of_rowband_destroy(of_rowband_t* ctx) {
     if (!ctx) return OF_OK;

@@ -17,8 +17,9 @@
 //
 // Sequence numbers only grow and a slot is reused after PEER_SLOTS collectives, while no rank can
 // run more than one collective ahead of the slowest one, so flags never need a reset.  Every spin
-// has a time-out (a peer that died must not hang the GPU): it sets a sticky error word that makes
-// all later waits fall through; the host reads it after the run.
+// has a time-out (a peer that died must not hang the GPU): it sets an error word that makes
+// all later waits of the run fall through; the host reads it after the run (of_rowband_trace /
+// of_rowband_status return OF_ERR_PEER_TIMEOUT) and the next run after that read starts with a clean word.
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -118,7 +119,12 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(const Allred
 
 }  // namespace
 
-__global__ void peer_bump_run_kernel(unsigned long long* run_id) { *run_id += 1; }
+// first kernel of a run: next run number; clear_err: the host has read the error word of an earlier run
+// (of_rowband_trace / of_rowband_status), so this run may wait for its peers again
+__global__ void peer_bump_run_kernel(unsigned long long* run_id, int* err, int clear_err) {
+    *run_id += 1;
+    if (clear_err) *err = 0;
+}
 
 void fill_peer_sync(PeerSync& s, const PeerView& pv, unsigned long long op) {
     for (int r = 0; r < PEER_MAX_WORLD; ++r) s.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
@@ -156,9 +162,9 @@ cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const f
     return cudaGetLastError();
 }
 
-cudaError_t launch_peer_begin_run(const PeerView& pv, int* launches, cudaStream_t stream) {
+cudaError_t launch_peer_begin_run(const PeerView& pv, bool clear_error, int* launches, cudaStream_t stream) {
     if (launches) *launches += 1;
-    OF_LAUNCH(peer_bump_run_kernel, 1, 1, 0, stream, const_cast<unsigned long long*>(pv.run_id));
+    OF_LAUNCH(peer_bump_run_kernel, 1, 1, 0, stream, const_cast<unsigned long long*>(pv.run_id), pv.err, clear_error ? 1 : 0);
     return cudaGetLastError();
 }
 

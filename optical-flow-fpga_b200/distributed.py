@@ -514,6 +514,11 @@ class PeerRowbands:
 
     def close(self):
         self.u = self.v = None
+        dist = _dist()
+        if self.world > 1 and dist is not None:
+            # the arena is mapped by every peer: nobody frees it while another rank may still store into it
+            self.torch.cuda.synchronize(self.device)
+            dist.barrier()
         self.ctx.close()
 
 

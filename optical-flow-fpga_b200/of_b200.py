@@ -30,6 +30,7 @@ _STATUS = {
     3: "unsupported",
     4: "no CUDA device",
     5: "out of device memory",
+    6: "peer time-out",
 }
 
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "of_kernel_launches": (C.c_longlong, []),
     "of_host_alloc_pinned": (_i, [C.POINTER(_vp), C.c_size_t]),
     "of_host_free_pinned": (_i, [_vp]),
+    "of_release_host_buffers": (_i, []),
     "of_gradients_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "of_lk_from_gradients_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "of_lk_single_scale_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
@@ -106,6 +108,7 @@ SIGNATURES = {
     "of_rowband_run": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "of_rowband_result": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "of_rowband_trace": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "of_rowband_status": (_i, [_vp, _vp]),
     "of_rowband_destroy": (_i, [_vp]),
 }
 
@@ -159,6 +162,28 @@ def _frame(a, name: str) -> np.ndarray:
     if arr.ndim != 2:
         raise ValueError(f"{name} must be a 2-D array, got shape {arr.shape}")
     return arr
+
+
+def _out_pair(out, shape, dtype=np.float32):
+    """Caller-supplied result buffers of a batched call: the C library writes through their raw pointers,
+    so anything but two distinct C-contiguous arrays of exactly `shape` / `dtype` would be an out-of-bounds
+    host write."""
+    try:
+        u, v = out
+    except Exception:
+        raise ValueError("out must be a pair (u, v) of arrays") from None
+    for name, a in (("out[0]", u), ("out[1]", v)):
+        if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or tuple(a.shape) != tuple(shape) \
+                or not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+            raise ValueError(f"{name} must be a writable C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+    if u is v or np.shares_memory(u, v):
+        raise ValueError("out[0] and out[1] must not overlap")
+    return u, v
+
+
+def release_host_buffers() -> None:
+    """Free the device buffers the host-buffer calls keep for the current device (re-allocated on demand)."""
+    _check(lib().of_release_host_buffers())
 
 
 def _same_shape(*arrs: np.ndarray) -> None:
@@ -229,7 +254,7 @@ def lk_single_scale_batch(prev, curr, window_size: int = 5, mode: Optional[int] 
     if out is None:
         u, v = np.empty_like(p), np.empty_like(p)
     else:
-        u, v = out
+        u, v = _out_pair(out, p.shape)
     m = default_mode() if mode is None else int(mode)
     _check(lib().of_lk_single_scale_f32(_ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, _window(window_size), m))
     return u, v
@@ -276,9 +301,11 @@ def lk_pyramidal_batch(
     mode: Optional[int] = None,
     scale_factor: float = 0.5,
     return_trace: bool = False,
+    out=None,
 ):
     """[B, H, W] stacks -> (u, v) stacks; optional trace = (iters_executed [B, L],
-    residuals [B, L, I, 2]) with level 0 = coarsest, like the reference's loop index."""
+    residuals [B, L, I, 2]) with level 0 = coarsest, like the reference's loop index.
+    out = (u, v): caller-supplied result stacks (e.g. pinned, so the library's copies overlap its kernels)."""
     p = np.ascontiguousarray(prev, dtype=np.float32)
     c = np.ascontiguousarray(curr, dtype=np.float32)
     if p.ndim != 3 or p.shape != c.shape:
@@ -287,7 +314,7 @@ def lk_pyramidal_batch(
         raise ValueError("only scale_factor = 0.5 (the reference's value) is supported")
     b, h, w = p.shape
     levels, iters = int(num_levels), int(num_iterations)
-    u, v = np.empty_like(p), np.empty_like(p)
+    u, v = (np.empty_like(p), np.empty_like(p)) if out is None else _out_pair(out, p.shape)
     wts = gaussian_weights(1.0 / scale_factor)
     it_exec = np.zeros((b, max(levels, 1)), np.int32)
     resid = np.zeros((b, max(levels, 1), max(iters, 1), 2), np.float32)
@@ -450,7 +477,7 @@ def lk_single_scale_u8_batch(prev_u8, curr_u8, window_size: int = 5, mode: Optio
     if p.ndim != 3 or p.shape != c.shape:
         raise ValueError("prev and curr must be [B, H, W] arrays of equal shape")
     b, h, w = p.shape
-    u, v = out if out is not None else (np.empty((b, h, w), np.float32), np.empty((b, h, w), np.float32))
+    u, v = _out_pair(out, (b, h, w)) if out is not None else (np.empty((b, h, w), np.float32), np.empty((b, h, w), np.float32))
     m = default_mode() if mode is None else int(mode)
     _check(lib().of_lk_single_scale_u8(_ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, _window(window_size), m))
     return u, v
@@ -653,12 +680,18 @@ class RowbandContext:
         return int(u.value), int(v.value)
 
     def trace(self, stream=0):
-        """(iters_executed[levels], residuals[levels, iterations, 2], error) after waiting for `stream`."""
+        """(iters_executed[levels], residuals[levels, iterations, 2], 0) after waiting for `stream`.
+        Raises OFBackendError if a peer rank did not answer within the time-out during the run (the flow of
+        that run is garbage); the next run starts clean."""
         iters = np.zeros(self.levels, dtype=np.int32)
         resid = np.zeros((self.levels, max(self.iterations, 1), 2), dtype=np.float32)
         err = C.c_int(0)
         _check(lib().of_rowband_trace(self._ctx, _ptr(iters), _ptr(resid) if self.iterations > 0 else None, C.byref(err), stream))
         return iters, resid[:, : self.iterations], int(err.value)
+
+    def status(self, stream=0) -> None:
+        """Waits for `stream`; raises OFBackendError if the run saw a peer time-out."""
+        _check(lib().of_rowband_status(self._ctx, stream))
 
     def close(self) -> None:
         if self._ctx:

@@ -8,12 +8,13 @@ integer oracle.
 """
 
 import hashlib
+import json
 import sys
 
 import numpy as np
 import pytest
 
-from conftest import BACKEND_DIR
+from conftest import BACKEND_DIR, ROOT
 
 sys.path.insert(0, str(BACKEND_DIR))
 
@@ -720,8 +721,9 @@ def test_peer_rowband_lanes_single_process(ofb):
 
 
 def test_native_rowband_driver_times_out_instead_of_hanging(ofb):
-    """A rank whose peer never shows up must not wedge the GPU: every spin has a time-out that sets a
-    sticky error word, the run drains, and of_rowband_trace reports it."""
+    """A rank whose peer never shows up must not wedge the GPU: every spin has a time-out that sets
+    the error word, the run drains, of_rowband_trace / of_rowband_status report OF_ERR_PEER_TIMEOUT, and the
+    run after that starts clean."""
     import time
 
     import torch
@@ -741,9 +743,28 @@ def test_native_rowband_driver_times_out_instead_of_hanging(ofb):
         st = torch.cuda.Stream(device=dev)
         t0 = time.perf_counter()
         ctxs[0].run(pd.data_ptr(), cd.data_ptr(), None, None, st.cuda_stream)  # rank 1 never runs
-        _, _, err = ctxs[0].trace(st.cuda_stream)
-        assert err == 1
+        with pytest.raises(ofb.OFBackendError, match="time-out"):
+            ctxs[0].trace(st.cuda_stream)
         assert time.perf_counter() - t0 < 5.0  # one time-out, then every later wait falls through
+        # The error has been reported, so the next run starts with a clean error word: both ranks run now
+        # (two streams of the one device); rank 0's sequence numbers are one run ahead of rank 1's, so rank 1
+        # runs twice -- its first run pairs with the run rank 0 gave up on.
+        s1 = torch.cuda.Stream(device=dev)
+        ctxs[1].run(pd.data_ptr(), cd.data_ptr(), None, None, s1.cuda_stream)
+        try:
+            ctxs[1].status(s1.cuda_stream)  # rank 0 abandoned that run half-way: rank 1 times out as well (40 ms)
+        except ofb.OFBackendError:
+            pass
+        for cx in ctxs:
+            cx.set_timeout_ms(4000)
+        u0, v0 = torch.empty_like(pd), torch.empty_like(pd)
+        ctxs[0].run(pd.data_ptr(), cd.data_ptr(), u0.data_ptr(), v0.data_ptr(), st.cuda_stream)
+        ctxs[1].run(pd.data_ptr(), cd.data_ptr(), None, None, s1.cuda_stream)
+        ctxs[0].status(st.cuda_stream)
+        ctxs[1].status(s1.cuda_stream)
+        u1, v1 = ofb.lk_pyramidal(prev[0], curr[0], 3, 5, 3, mode=ofb.MODE_FAST)
+        assert_bit_equal(u0.cpu().numpy(), u1, "run after a reported time-out, u")
+        assert_bit_equal(v0.cpu().numpy(), v1, "run after a reported time-out, v")
     finally:
         for cx in ctxs:
             cx.close()
@@ -856,3 +877,35 @@ def test_8k_single_scale_locality_and_unaligned_base(ofb):
     uo, vo = orc.lucas_kanade_single_scale(prev[0][:h, :w], curr[0][:h, :w], 5)
     assert_bit_equal(out_u.cpu().numpy().reshape(h, w), uo, "unaligned base u")
     assert_bit_equal(out_v.cpu().numpy().reshape(h, w), vo, "unaligned base v")
+
+
+def _visible_gpus() -> int:
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("mode_name", ["fast", "exact"])
+def test_rowband_over_real_nvlink_multi_process(ofb, mode_name):
+    """The row-band driver between real GPUs: one process per GPU under torch.distributed.run, arenas mapped
+    through CUDA IPC, collectives by peer stores inside the kernels (tests/run_rowband_nccl.py --driver peer).
+    Rank 0 asserts the gathered flow equals the single-GPU driver bit for bit.  Needs > 1 visible GPU: on the
+    one-GPU box of the round-end suite it skips (the emulated-ranks test above covers the logic there)."""
+    import socket
+    import subprocess
+
+    n = _visible_gpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "run_rowband_nccl.py"), "--height", "1080", "--width", "1920",
+           "--levels", "4", "--iters", "4", "--mode", mode_name, "--driver", "peer", "--repeat", "2"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == world and out["bit_equal_to_single_gpu"] is True
