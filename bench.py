@@ -105,13 +105,16 @@ def ncu_traffic_bytes(workload: str, batch: int):
         return None, None
 
 
-def pyramidal_bytes_per_pixel(levels: int, iters: int) -> float:
+def pyramidal_bytes_per_pixel(levels: int, iters, executed=None) -> float:
     """Stage-fused traffic model of SURVEY.md 8(d), N_l = N / 4^l (l = 0 finest): pyramid 2 frames x
-    (N_{l-1} + N_l) x 4 B for l >= 1; 24 B per iteration and level pixel; upsample 8 B x N_{l+1}, i.e. per
-    COARSE pixel of every level transition.  3 levels x 3 iterations: 109.5 B/pixel; 5 x 10: 335.6."""
+    (N_{l-1} + N_l) x 4 B for l >= 1; 24 B per EXECUTED iteration and level pixel; upsample 8 B x N_{l+1}, i.e.
+    per COARSE pixel of every level transition.  3 levels x 3 iterations: 109.5 B/pixel; 5 x 10: 335.6.
+    executed: mean executed iterations per level, index 0 = COARSEST (the reference's level index) -- the
+    reference's early exit (mean|du|, mean|dv| < 0.01) ends a level before `iters`; only executed ones count."""
     n = [1.0 / 4**l for l in range(levels)]
+    per_level = [float(iters)] * levels if executed is None else [float(executed[levels - 1 - l]) for l in range(levels)]
     b = sum(2 * (n[l - 1] + n[l]) * 4 for l in range(1, levels))
-    b += sum(24 * iters * n[l] for l in range(levels))
+    b += sum(24 * per_level[l] * n[l] for l in range(levels))
     b += sum(8 * n[l + 1] for l in range(levels - 1))
     return b
 
@@ -622,6 +625,23 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
             enqueue()
             torch.cuda.synchronize()
             launches = (of_b200.kernel_launches() - l0) * steps
+    # iterations the reference's early exit let every level run (pyramidal workloads): one more, untimed pass
+    executed = None
+    if wl["pyramidal"]:
+        L, I = wl["levels"], wl["iters"]
+        if lanes is not None:
+            tr = lanes.trace()  # per lane: the last pair it ran
+            executed = np.mean(np.stack([np.asarray(t[0], dtype=np.float64) for t in tr]), axis=0)
+        elif not rowband:
+            it_dev = torch.zeros((B, L), dtype=torch.int32, device=dev)
+            of_b200.lk_pyramidal_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, L, WINDOW, I,
+                                     pyr_mode, ws.data_ptr(), ws_bytes, it_dev.data_ptr(), None, stream)
+            torch.cuda.synchronize()
+            executed = it_dev.to(torch.float64).mean(dim=0).cpu().numpy()
+        if executed is not None and world > 1 and not rowband:
+            t_ex = torch.tensor(executed, dtype=torch.float64, device=dev)
+            dist.all_reduce(t_ex)
+            executed = (t_ex / world).cpu().numpy()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
     ms_per_step = env.max_over_ranks(total_ms) / steps
@@ -641,7 +661,8 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
     if lanes is not None:
         lanes.close()
     peak, peak_src = hbm_peak()
-    bpp = pyramidal_bytes_per_pixel(wl["levels"], wl["iters"]) if wl["pyramidal"] else {"fixed": 6.0, "u8": 10.0}.get(variant, 16.0)
+    bpp = (pyramidal_bytes_per_pixel(wl["levels"], wl["iters"], executed) if wl["pyramidal"]
+           else {"fixed": 6.0, "u8": 10.0}.get(variant, 16.0))
     kernel_ms = statistics.mean(per_step)
     # per-GPU figure: in row-band mode the ranks share the step's pixels
     achieved = bpp * pixels_per_step / (world if rowband else 1) / (kernel_ms * 1e-3) / 1e9
@@ -671,6 +692,9 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
             "algorithmic_bytes": bpp * pixels_per_step,
             "peak_source": peak_src,
             "algorithmic_bytes_per_pixel": bpp,
+            "algorithmic_bytes_per_pixel_if_every_iteration_ran": (pyramidal_bytes_per_pixel(wl["levels"], wl["iters"])
+                                                                   if wl["pyramidal"] else None),
+            "iterations_executed_per_level_coarse_to_fine": None if executed is None else [float(x) for x in executed],
             "kernel": kernel,
             "kernel_ms": kernel_ms,
             "frac_of_nominal_8TBs": achieved / 8000.0,

@@ -97,6 +97,25 @@ struct HostPath {
     Arena arena;
     cudaStream_t streams[HOST_STREAMS] = {nullptr, nullptr, nullptr};
     int device = -1;
+    // small page-locked staging buffer: a device->host copy into pageable memory blocks the calling thread
+    // until it has completed, which would serialise the pipelined passes
+    void* staging = nullptr;
+    size_t staging_cap = 0;
+    int get_staging(size_t bytes, void** out) {
+        if (staging_cap < bytes) {
+            if (staging) cudaFreeHost(staging);
+            staging = nullptr;
+            staging_cap = 0;
+            cudaError_t e = cudaHostAlloc(&staging, bytes ? bytes : 1, cudaHostAllocDefault);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(OF_ERR_OUT_OF_MEMORY, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+            }
+            staging_cap = bytes;
+        }
+        *out = staging;
+        return OF_OK;
+    }
     // every stream drained: called before a host entry point returns, on success and on failure, so no
     // copy into the caller's or the arena's buffers is in flight once the mutex is released
     cudaError_t drain() {
@@ -479,6 +498,9 @@ int of_release_host_buffers(void) {
     std::lock_guard<std::mutex> lock(hp->mutex);
     if (hp->drain() != cudaSuccess) cudaGetLastError();
     hp->arena.release();
+    if (hp->staging) cudaFreeHost(hp->staging);
+    hp->staging = nullptr;
+    hp->staging_cap = 0;
     return OF_OK;
 }
 
@@ -724,6 +746,14 @@ int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v
         if (iters_executed) OF_TRY(hp->arena.get(base + 5, ib, reinterpret_cast<void**>(&d_iters[s])));
         if (residuals) OF_TRY(hp->arena.get(base + 6, rb, reinterpret_cast<void**>(&d_res[s])));
     }
+    // the per-pair trace (a few bytes) goes through page-locked staging memory and reaches the caller's
+    // arrays after the last pass: a copy into pageable memory would stall the pipeline at every pass
+    const size_t it_total = iters_executed ? (size_t)batch * levels * sizeof(int) : 0;
+    const size_t rs_total = (residuals && iterations > 0) ? (size_t)batch * levels * iterations * 2 * sizeof(float) : 0;
+    char* stage_mem = nullptr;
+    if (it_total + rs_total) OF_TRY(hp->get_staging(it_total + rs_total, reinterpret_cast<void**>(&stage_mem)));
+    int* st_iters = reinterpret_cast<int*>(stage_mem);
+    float* st_res = reinterpret_cast<float*>(stage_mem + it_total);
     for (int c = 0; c < n_pass; ++c) {
         const int s = c % slots;
         cudaStream_t st = hp->streams[s];
@@ -738,14 +768,16 @@ int of_lk_pyramidal_f32(const float* prev, const float* curr, float* u, float* v
                              gauss_weights, gauss_radius, ws[s], pp.total, d_iters[s], d_res[s], st, cnt));
         OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d[s][2], bytes, cudaMemcpyDeviceToHost, st));
         OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d[s][3], bytes, cudaMemcpyDeviceToHost, st));
-        if (iters_executed)
-            OF_CUDA(cudaMemcpyAsync(iters_executed + b0 * levels, d_iters[s], (size_t)nb * levels * sizeof(int),
+        if (it_total)
+            OF_CUDA(cudaMemcpyAsync(st_iters + b0 * levels, d_iters[s], (size_t)nb * levels * sizeof(int),
                                     cudaMemcpyDeviceToHost, st));
-        if (residuals && iterations > 0)
-            OF_CUDA(cudaMemcpyAsync(residuals + b0 * levels * iterations * 2, d_res[s],
+        if (rs_total)
+            OF_CUDA(cudaMemcpyAsync(st_res + b0 * levels * iterations * 2, d_res[s],
                                     (size_t)nb * levels * iterations * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(hp->streams[s]));
+    if (it_total) memcpy(iters_executed, st_iters, it_total);
+    if (rs_total) memcpy(residuals, st_res, rs_total);
     return OF_OK;
 }
 

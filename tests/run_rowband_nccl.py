@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--mode", choices=["exact", "fast"], default="fast")
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--timeline", default="", help="write rank 0's kernel timeline of one more run (CUPTI through torch.profiler) "
+                    "to this CSV: analysis only, never a bench number")
     ap.add_argument("--driver", choices=["nccl", "peer"], default="peer",
                     help="nccl: Python loop + NCCL collectives; peer: native driver, peer-memory collectives")
     args = ap.parse_args()
@@ -69,6 +71,22 @@ def main():
     if plan is not None:
         plan.trace()  # raises if a peer wait timed out
     times = times[1:]
+    if args.timeline and plan is not None:
+        from torch.profiler import ProfilerActivity, profile
+
+        dist.barrier()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            plan.run(pd, cd)
+            torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            evs = sorted((e for e in prof.events() if e.device_type.name == "CUDA"), key=lambda e: e.time_range.start)
+            t0 = evs[0].time_range.start if evs else 0
+            with open(args.timeline, "w") as f:
+                f.write("start_us,duration_us,name\n")
+                for e in evs:
+                    f.write(f"{e.time_range.start - t0:.1f},{e.time_range.end - e.time_range.start:.1f},{e.name[:60]}\n")
     u, v = ud.cpu().numpy(), vd.cpu().numpy()
     ok = None
     t_single = None
