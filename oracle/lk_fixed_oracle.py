@@ -5,11 +5,18 @@ Integer restatement of the reference's single-scale RTL datapath
 on geometrically correct 3x3 / 5x5 windows.  Only ``tests/``, ``smoke()`` and
 ``bench.py``'s CPU-baseline leg import it.
 
-PARITY UNPINNED: the reference holds no runnable golden for this datapath.  There
-is no SystemVerilog simulator in the build image, and the only known-answer data
-(the XSim log pasted in the reference's ``README.md:455-532``) predates the
-committed RTL and cannot be reproduced from it.  The
-arithmetic below is therefore pinned by reading the RTL source, line by line:
+PARITY: PINNED BY THE RTL TEXT, NOT BY A SIMULATOR RUN ("parity unpinned" in the task's strict sense).
+The reference holds no runnable golden for this datapath: there is no SystemVerilog simulator in the
+build image, and the only known-answer data (the XSim log pasted in the reference's
+``README.md:455-532``) predates the committed RTL and cannot be reproduced from it.
+What pins the arithmetic below is mechanical all the same: ``oracle/sv_eval.py`` parses
+``gradient_compute.sv`` / ``window_accumulator.sv`` / ``flow_solver.sv`` and EXECUTES their
+``always_comb`` / ``always_ff`` bodies from the source text under IEEE 1800-2017's expression sizing and
+signedness rules (checked on the standard's own examples), and ``tests/test_fixed_oracle_vs_rtl_text.py``
+diffs this file against it on randomised neighbourhoods and solver inputs -- every integer equal; the
+vectors are committed as ``tests/golden/fx_rtl_text_vectors.npz`` and the GPU kernels are checked against
+them.  Until an XSim / Verilator dump of the committed RTL is diffed (``of_export_flow_fx_txt`` writes the
+testbench's format for that), the line-by-line reading that the evaluator reproduces is:
 
 * pixels sit in ``logic signed [7:0]`` windows; ``avg = (curr + prev) >> 1`` is
   evaluated in 9 bits with both operands SIGN-extended and a LOGICAL shift

@@ -23,6 +23,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tests" / "host_emul"))
 
 CHILD = r"""
+import os
 import sys
 import numpy as np
 sys.path.insert(0, {root!r}); sys.path.insert(0, {backend!r})
@@ -73,6 +74,15 @@ assert all(same(u[b], want[b][0]) and same(v[b], want[b][1]) for b in range(3))
 u16, v16 = of_b200.lk_single_scale_fx(p8[0], c8[0])
 uo, vo = fxo.lk_single_scale_fx(p8[0], c8[0])
 assert np.array_equal(u16, uo) and np.array_equal(v16, vo)
+# the fixed-point kernels' sources against vectors produced by executing the reference's RTL text (oracle/sv_eval.py):
+# marching kernel (width % 16 == 0) and tile kernel (one column more)
+zz = np.load(os.path.join(os.path.dirname(os.path.abspath(fxo.__file__)), "..", "tests", "golden", "fx_rtl_text_vectors.npz"))
+for extra in (0, 1):
+    fpv = np.ascontiguousarray(np.pad(zz["frame_prev"], ((0, 0), (0, extra)), constant_values=128))
+    fcv = np.ascontiguousarray(np.pad(zz["frame_curr"], ((0, 0), (0, extra)), constant_values=128))
+    u16, v16 = of_b200.lk_single_scale_fx(fpv, fcv)
+    assert np.array_equal(u16[zz["centres"][:, 0], zz["centres"][:, 1]], zz["u"]), "RTL-text vectors, u"
+    assert np.array_equal(v16[zz["centres"][:, 0], zz["centres"][:, 1]], zz["v"]), "RTL-text vectors, v"
 
 # the pyramidal driver: 3 levels x 3 iterations, exact mode bit for bit (levels 64x96, 32x48, 16x24: marching pyramid
 # kernel / tile pyramid kernel, split refinement), a batch whose second pair converges early, the drop-in module

@@ -909,3 +909,23 @@ def test_rowband_over_real_nvlink_multi_process(ofb, mode_name):
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
     out = json.loads(line)
     assert out["world"] == world and out["bit_equal_to_single_gpu"] is True
+
+
+@pytest.mark.parametrize("kernel", ["march", "tile"])
+def test_fixed_point_mode_against_rtl_text_vectors(ofb, kernel):
+    """a8 against vectors that were produced by executing the reference's RTL text (oracle/sv_eval.py on
+    gradient_compute.sv / window_accumulator.sv / flow_solver.sv, tests/golden/make_golden_fx_rtl_text.py): 320
+    neighbourhoods tiled into one frame pair, S8.7 flow compared at the patch centres; both kernels (the frame's width
+    is a multiple of 16 -> marching kernel; one column more -> tile kernel)."""
+    from conftest import GOLDEN
+
+    z = np.load(GOLDEN / "fx_rtl_text_vectors.npz")
+    fp, fc = z["frame_prev"], z["frame_curr"]
+    if kernel == "tile":
+        fp = np.ascontiguousarray(np.pad(fp, ((0, 0), (0, 1)), constant_values=128))
+        fc = np.ascontiguousarray(np.pad(fc, ((0, 0), (0, 1)), constant_values=128))
+    u, v = ofb.lk_single_scale_fx(fp, fc)
+    cy, cx = z["centres"][:, 0], z["centres"][:, 1]
+    assert_bit_equal(u[cy, cx], z["u"], f"u at the patch centres ({kernel})")
+    assert_bit_equal(v[cy, cx], z["v"], f"v at the patch centres ({kernel})")
+    assert int((np.abs(z["u"].astype(np.int32)) + np.abs(z["v"].astype(np.int32)) > 0).sum()) > 100
