@@ -198,14 +198,17 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
                              int W, int* launches, cudaStream_t stream);
 // fused Gaussian (separable, float64 accumulate, float32 store per axis, reflect) + bilinear
 // resample on the np.linspace grid (lucas_kanade_pyramidal.py:44-59)
-// fast = true (fast mode of the pyramidal drivers only): fused multiply-adds in the float64 filter
+// fast = true (fast mode of the pyramidal drivers only): the marching kernel's float32 flavour
+// (OF_B200_PYRAMID_FAST=f64: float64 with fused multiply-adds, the former fast flavour, for A/B runs)
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
                                 const double* weights, int radius, int row_lo, int row_hi, int* launches,
                                 cudaStream_t stream, bool fast = false);
 // the same level by the marching kernel (pyramid_march.cu): radius 8, decimation step in [1, 6]
 bool pyramid_march_supported(int H, int W, int oh, int ow, int radius);
+// flavour: 0 = SciPy's bits (separate float64 multiplies and adds), 1 = float64 with fused multiply-adds,
+// 2 = float32 with fused multiply-adds (fast mode's default: no conversions, a quarter of the pipe time)
 cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
-                                 const double* weights, int row_lo, int row_hi, bool fused_multiply_add, int* launches,
+                                 const double* weights, int row_lo, int row_hi, int flavour, int* launches,
                                  cudaStream_t stream);
 cudaError_t launch_warp(const float* img, const float* fu, const float* fv, float* out, int batch, int H, int W,
                         int* launches, cudaStream_t stream);

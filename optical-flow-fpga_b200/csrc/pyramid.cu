@@ -229,8 +229,13 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
         const char* e = getenv("OF_B200_PYRAMID");
         return e != nullptr && strcmp(e, "tile") == 0;
     }();
+    static const int fast_flavour = [] {
+        const char* e = getenv("OF_B200_PYRAMID_FAST");  // f64: float64 + FMA (the former fast flavour), for A/B runs
+        return (e != nullptr && strcmp(e, "f64") == 0) ? 1 : 2;
+    }();
     if (!force_tile && pyramid_march_supported(H, W, oh, ow, radius))
-        return launch_pyramid_march(src, dst, batch, H, W, oh, ow, weights, row_lo, row_hi, fast, launches, stream);
+        return launch_pyramid_march(src, dst, batch, H, W, oh, ow, weights, row_lo, row_hi, fast ? fast_flavour : 0, launches,
+                                    stream);
     PyrArgs a;
     a.src = src;
     a.dst = dst;

@@ -22,6 +22,8 @@
 // SM), not by HBM (5 B per fine pixel).
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "of_common.cuh"
 #include "of_kernels.h"
 
@@ -78,14 +80,45 @@ __device__ __forceinline__ double pm_gauss(const double* x, const double* w) {
     }
     return acc;
 }
-
+// float32 flavour (PM_F32, default of the fast pyramidal drivers): the same symmetric order with float32 fused
+// multiply-adds -- no conversions, a quarter of the pipe time.  A smoothed value then carries a few float32
+// roundings (about 2 ulp, 3e-5 on a 0..255 image) instead of one.
 template <bool FMA>
+__device__ __forceinline__ float pm_gauss(const float* x, const float* w) {
+    float acc = fmul(x[PM_R], w[PM_R]);
+#pragma unroll
+    for (int ii = -PM_R; ii < 0; ++ii) acc = fmaf(fadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R], acc);
+    return acc;
+}
+
+// flavours of the kernel: SciPy's bits; float64 with fused multiply-adds; float32
+enum { PM_EXACT = 0, PM_F64_FMA = 1, PM_F32 = 2 };
+template <typename A> struct PmPair;
+template <> struct PmPair<double> { typedef double2 type; };
+template <> struct PmPair<float> { typedef float2 type; };
+
+template <int FLAVOUR>
 __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrMarchArgs a) {
+    constexpr bool FMA = FLAVOUR != PM_EXACT;
+    typedef typename std::conditional<FLAVOUR == PM_F32, float, double>::type A;  // accumulator / register type
+    typedef typename PmPair<A>::type A2;
     OF_DYNAMIC_SMEM_ALIGNED(16, unsigned char, pm_smem);
-    // axis-0 results of two consecutive steps, already rounded to float32 but kept as float64 so
-    // that the axis-1 pass needs no conversions; then the ring of fully smoothed rows (float32)
-    double* tmp = reinterpret_cast<double*>(pm_smem);                               // [2][PM_CH][PM_TPITCH]
+    // axis-0 results of two consecutive steps, already rounded to float32 but kept in the accumulator type
+    // so that the axis-1 pass needs no conversions; then the ring of fully smoothed rows (float32)
+    A* tmp = reinterpret_cast<A*>(pm_smem);                                         // [2][PM_CH][PM_TPITCH]
     float* smo = reinterpret_cast<float*>(pm_smem + PM_TMP_BYTES);                  // [PM_RING][PM_SPITCH]
+    A wt[2 * PM_R + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * PM_R + 1; ++k) wt[k] = (A)a.w[k];
+    if (FLAVOUR == PM_F32) {
+        // rounding 17 weights to float32 leaves their sum ~1e-8 off 1 -- a bias of that relative size in every
+        // smoothed value; the centre tap absorbs it (weights that sum to 1 within half an ulp of the centre tap)
+        double others = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * PM_R + 1; ++k)
+            if (k != PM_R) others += (double)wt[k];
+        wt[PM_R] = (A)(1.0 - others);
+    }
 
     const int H = a.H, W = a.W, tid = threadIdx.x;
     const float* __restrict__ src = a.src + (size_t)blockIdx.z * H * W;
@@ -106,9 +139,9 @@ __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrM
     // axis 0: this thread's source column (reflected at the frame edge)
     const float* __restrict__ colp = src + pm_reflect(cx0 - PM_R + tid, W);
 
-    double x[PM_CH + 2 * PM_R];  // source rows ybase - 8 .. ybase + 15 of this column
+    A x[PM_CH + 2 * PM_R];  // source rows ybase - 8 .. ybase + 15 of this column
 #pragma unroll
-    for (int k = 0; k < 2 * PM_R; ++k) x[k] = (double)__ldg(colp + (size_t)pm_reflect(y_first - PM_R + k, H) * W);
+    for (int k = 0; k < 2 * PM_R; ++k) x[k] = (A)__ldg(colp + (size_t)pm_reflect(y_first - PM_R + k, H) * W);
     float nxt[PM_CH];
 #pragma unroll
     for (int k = 0; k < PM_CH; ++k) nxt[k] = __ldg(colp + (size_t)pm_reflect(y_first + PM_R + k, H) * W);
@@ -135,32 +168,32 @@ __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrM
         if (it < n_steps) {
             const int ybase = y_first + it * PM_CH;
 #pragma unroll
-            for (int k = 0; k < PM_CH; ++k) x[2 * PM_R + k] = (double)nxt[k];
+            for (int k = 0; k < PM_CH; ++k) x[2 * PM_R + k] = (A)nxt[k];
             if (it + 1 < n_steps) {
 #pragma unroll
                 for (int k = 0; k < PM_CH; ++k)
                     nxt[k] = __ldg(colp + (size_t)pm_reflect(ybase + PM_CH + PM_R + k, H) * W);
             }
-            double* tw = tmp + (it & 1) * (PM_CH * PM_TPITCH) + tid;
+            A* tw = tmp + (it & 1) * (PM_CH * PM_TPITCH) + tid;
 #pragma unroll
-            for (int k = 0; k < PM_CH; ++k) tw[k * PM_TPITCH] = (double)(float)pm_gauss<FMA>(x + k, a.w);
+            for (int k = 0; k < PM_CH; ++k) tw[k * PM_TPITCH] = (A)(float)pm_gauss<FMA>(x + k, wt);
 #pragma unroll
             for (int k = 0; k < 2 * PM_R; ++k) x[k] = x[k + PM_CH];
         }
         if (it >= 1 && it - 1 < n_steps && hseg < PM_NSEG) {
             const int hs = it - 1;
-            const double2* row2 =
-                reinterpret_cast<const double2*>(tmp + (hs & 1) * (PM_CH * PM_TPITCH) + hk * PM_TPITCH + hseg * PM_SEG);
-            double t[PM_SEG + 2 * PM_R];
+            const A2* row2 =
+                reinterpret_cast<const A2*>(tmp + (hs & 1) * (PM_CH * PM_TPITCH) + hk * PM_TPITCH + hseg * PM_SEG);
+            A t[PM_SEG + 2 * PM_R];
 #pragma unroll
             for (int q = 0; q < (PM_SEG + 2 * PM_R) / 2; ++q) {
-                const double2 f = row2[q];
+                const A2 f = row2[q];
                 t[2 * q + 0] = f.x;
                 t[2 * q + 1] = f.y;
             }
             float o[PM_SEG];
 #pragma unroll
-            for (int k = 0; k < PM_SEG; ++k) o[k] = (float)pm_gauss<FMA>(t + k, a.w);
+            for (int k = 0; k < PM_SEG; ++k) o[k] = (float)pm_gauss<FMA>(t + k, wt);
             float4* out4 = reinterpret_cast<float4*>(smo + ((hs * PM_CH + hk) & (PM_RING - 1)) * PM_SPITCH + hseg * PM_SEG);
             out4[0] = make_float4(o[0], o[1], o[2], o[3]);
             out4[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -188,12 +221,20 @@ __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrM
                     const int y1 = min(y0 + 1, H - 1);
                     const float* s0 = smo + ((y0 - y_first) & (PM_RING - 1)) * PM_SPITCH;
                     const float* s1 = smo + ((y1 - y_first) & (PM_RING - 1)) * PM_SPITCH;
-                    double t = 0.0;
-                    t = dadd(t, dmul(dmul((double)s0[x0], wy0), wx0));
-                    t = dadd(t, dmul(dmul((double)s0[x1], wy0), fx));
-                    t = dadd(t, dmul(dmul((double)s1[x0], fy), wx0));
-                    t = dadd(t, dmul(dmul((double)s1[x1], fy), fx));
-                    dst[(size_t)i * a.ow + j] = (float)t;
+                    if (FLAVOUR == PM_F32) {
+                        // float32 lerps with the float64 grid fractions rounded once
+                        const float ffx = (float)fx, ffy = (float)fy;
+                        const float top = fmaf(ffx, fsub(s0[x1], s0[x0]), s0[x0]);
+                        const float bot = fmaf(ffx, fsub(s1[x1], s1[x0]), s1[x0]);
+                        dst[(size_t)i * a.ow + j] = fmaf(ffy, fsub(bot, top), top);
+                    } else {
+                        double t = 0.0;
+                        t = dadd(t, dmul(dmul((double)s0[x0], wy0), wx0));
+                        t = dadd(t, dmul(dmul((double)s0[x1], wy0), fx));
+                        t = dadd(t, dmul(dmul((double)s1[x0], fy), wx0));
+                        t = dadd(t, dmul(dmul((double)s1[x1], fy), fx));
+                        dst[(size_t)i * a.ow + j] = (float)t;
+                    }
                 }
             }
             next_i = i_end;
@@ -212,8 +253,9 @@ bool pyramid_march_supported(int H, int W, int oh, int ow, int radius) {
 }
 
 cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
-                                 const double* weights, int row_lo, int row_hi, bool fused_multiply_add, int* launches,
+                                 const double* weights, int row_lo, int row_hi, int flavour, int* launches,
                                  cudaStream_t stream) {
+    if (flavour < PM_EXACT || flavour > PM_F32) return cudaErrorInvalidValue;
     if (batch > 65535 || row_lo < 0 || row_hi > oh || row_lo >= row_hi) return cudaErrorInvalidValue;
     PyrMarchArgs a;
     a.src = src;
@@ -252,18 +294,21 @@ cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H,
         }
     }
     const int n_bands = (rows + a.band_rows - 1) / a.band_rows;
-    static SmemOptIn opt_in[2];
+    static SmemOptIn opt_in[3];
     {
-        cudaError_t e = fused_multiply_add ? opt_in[1].ensure(pyramid_march_kernel<true>, PM_SMEM_BYTES)
-                                           : opt_in[0].ensure(pyramid_march_kernel<false>, PM_SMEM_BYTES);
+        cudaError_t e = flavour == PM_F32       ? opt_in[2].ensure(pyramid_march_kernel<PM_F32>, PM_SMEM_BYTES)
+                        : flavour == PM_F64_FMA ? opt_in[1].ensure(pyramid_march_kernel<PM_F64_FMA>, PM_SMEM_BYTES)
+                                                : opt_in[0].ensure(pyramid_march_kernel<PM_EXACT>, PM_SMEM_BYTES);
         if (e != cudaSuccess) return e;
     }
     if (launches) *launches += 1;
     dim3 grid(n_strips, n_bands, batch);
-    if (fused_multiply_add)
-        OF_LAUNCH(pyramid_march_kernel<true>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
+    if (flavour == PM_F32)
+        OF_LAUNCH(pyramid_march_kernel<PM_F32>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
+    else if (flavour == PM_F64_FMA)
+        OF_LAUNCH(pyramid_march_kernel<PM_F64_FMA>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
     else
-        OF_LAUNCH(pyramid_march_kernel<false>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
+        OF_LAUNCH(pyramid_march_kernel<PM_EXACT>, grid, PM_THREADS, PM_SMEM_BYTES, stream, a);
     return cudaGetLastError();
 }
 

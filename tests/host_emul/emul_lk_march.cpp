@@ -84,37 +84,7 @@ static inline void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int 
 #define OF_KEEP_ALIVE_L(x) (void)(x)
 #define OF_PREFETCH_L2(p) (void)(p)
 
-// ---- packed pairs ------------------------------------------------------------------------------------------
-typedef unsigned long long f32x2;
-static inline f32x2 pk(float lo, float hi) {
-    unsigned a, b;
-    std::memcpy(&a, &lo, 4);
-    std::memcpy(&b, &hi, 4);
-    return ((f32x2)b << 32) | a;
-}
-static inline void unpk(f32x2 v, float& lo, float& hi) {
-    const unsigned a = (unsigned)v, b = (unsigned)(v >> 32);
-    std::memcpy(&lo, &a, 4);
-    std::memcpy(&hi, &b, 4);
-}
-#define OF_PAIR_OP(name, expr_lo, expr_hi)                   \
-    static inline f32x2 name(f32x2 a, f32x2 b) {              \
-        float al, ah, bl, bh;                                 \
-        unpk(a, al, ah);                                      \
-        unpk(b, bl, bh);                                      \
-        volatile float rl = expr_lo, rh = expr_hi;            \
-        return pk(rl, rh);                                    \
-    }
-OF_PAIR_OP(add2, al + bl, ah + bh)
-OF_PAIR_OP(sub2, al - bl, ah - bh)
-OF_PAIR_OP(mul2, al* bl, ah* bh)
-static inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    float al, ah, bl, bh, cl, ch;
-    unpk(a, al, ah);
-    unpk(b, bl, bh);
-    unpk(c, cl, ch);
-    return pk(std::fmaf(al, bl, cl), std::fmaf(ah, bh, ch));
-}
+// ---- packed pairs: host stand-ins in csrc/f32x2.cuh (two IEEE float32 operations each) ------------------------
 static inline float rcp_approx(float x) { volatile float r = 1.0f / x; return r; }
 static inline double rcp_approx_f64(double x) { volatile double r = 1.0 / x; return r; }
 
