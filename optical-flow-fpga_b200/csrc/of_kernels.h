@@ -198,15 +198,15 @@ cudaError_t launch_gradients(const float* prev, const float* curr, float* ix, fl
                              int W, int* launches, cudaStream_t stream);
 // fused Gaussian (separable, float64 accumulate, float32 store per axis, reflect) + bilinear
 // resample on the np.linspace grid (lucas_kanade_pyramidal.py:44-59)
-// fast = true (fast mode of the pyramidal drivers only): the marching kernel's float32 flavour
-// (OF_B200_PYRAMID_FAST=f64: float64 with fused multiply-adds, the former fast flavour, for A/B runs)
+// fast = true (fast mode of the pyramidal drivers only): fused multiply-adds in the float64 filter
+// (OF_B200_PYRAMID_FAST=f32: the marching kernel's float32 flavour, an experiment -- faster, less faithful)
 cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
                                 const double* weights, int radius, int row_lo, int row_hi, int* launches,
                                 cudaStream_t stream, bool fast = false);
 // the same level by the marching kernel (pyramid_march.cu): radius 8, decimation step in [1, 6]
 bool pyramid_march_supported(int H, int W, int oh, int ow, int radius);
 // flavour: 0 = SciPy's bits (separate float64 multiplies and adds), 1 = float64 with fused multiply-adds,
-// 2 = float32 with fused multiply-adds (fast mode's default: no conversions, a quarter of the pipe time)
+// 2 = float32 with fused multiply-adds (experiment, OF_B200_PYRAMID_FAST=f32: no conversions, a quarter of the pipe time)
 cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H, int W, int oh, int ow,
                                  const double* weights, int row_lo, int row_hi, int flavour, int* launches,
                                  cudaStream_t stream);
@@ -240,6 +240,10 @@ cudaError_t launch_peer_begin_run(const PeerView& pv, bool clear_error, int* lau
 cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
                                   size_t dst_off, size_t first, size_t count, bool skip_self, int* launches,
                                   cudaStream_t stream);
+// the same with one element range [lo[r], hi[r]) per receiving rank (clipped to [first, first + count)): a halo push
+cudaError_t launch_peer_push_ranges(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
+                                    size_t dst_off, size_t first, size_t count, const size_t* lo, const size_t* hi,
+                                    int* launches, cudaStream_t stream);
 // signal collective `op` of the current run to every rank and wait for every rank's
 cudaError_t launch_peer_sync(const PeerView& pv, unsigned long long op, int* launches, cudaStream_t stream);
 // all-reduce of (sum|du|, sum|dv|) + the reference's convergence test + ping-pong flip, in one kernel

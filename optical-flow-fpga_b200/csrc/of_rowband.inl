@@ -421,7 +421,35 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         // (a replicated level stays in its ping-pong buffers; only the finest one is copied, locally,
         // to where of_rowband_result points)
         const size_t first = (size_t)a * w, count = (size_t)(b - a) * w;
-        if (!repl) {
+        if (!repl && k > 0) {
+            // Flow of a coarser level: a rank needs only the coarse rows its upsample of level k - 1 reads -- its
+            // own band plus the halo of its extended band -- so every rank receives just that part of my rows
+            // (a halo exchange with the neighbours; all of it only when the bands are thinner than the halo).
+            size_t lo_el[PEER_MAX_WORLD], hi_el[PEER_MAX_WORLD];
+            const int hf = c.h[k - 1];
+            const double sy = hf > 1 ? (double)(h - 1) / (double)(hf - 1) : 0.0;  // np.linspace step of upsample_flow
+            const int reach = RB_GROW * (iters > 1 ? iters : 1) + RB_GROW;
+            for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+                lo_el[r] = hi_el[r] = 0;
+                if (r >= world) continue;
+                int fa, fb;
+                rb_shard(hf, r, world, &fa, &fb);
+                if (fb <= fa) continue;
+                const int flo = fa - reach < 0 ? 0 : fa - reach, fhi = fb + reach > hf ? hf : fb + reach;
+                // target rows [flo, fhi) blend coarse rows floor(y * sy) and the one below; one row of margin
+                // on both sides (the product y * sy may round across an integer)
+                long long need_lo = (long long)floor((double)flo * sy) - 1;
+                long long need_hi = (long long)floor((double)(fhi - 1) * sy) + 3;
+                if (need_lo < 0) need_lo = 0;
+                if (need_hi > h) need_hi = h;
+                lo_el[r] = (size_t)need_lo * w;
+                hi_el[r] = (size_t)need_hi * w;
+            }
+            OF_CUDA(launch_peer_push_ranges(pv, fu(k, 0), fu(k, 1), sel_k, start, c.gu_off[k], first, count, lo_el, hi_el, &cnt.n, st));
+            OF_CUDA(launch_peer_push_ranges(pv, fv(k, 0), fv(k, 1), sel_k, start, c.gv_off[k], first, count, lo_el, hi_el, &cnt.n, st));
+            if (world > 1) OF_CUDA(launch_peer_sync(pv, op++, &cnt.n, st));
+        } else if (!repl) {
+            // the finest level: the final gather, every rank receives the whole flow
             OF_CUDA(launch_peer_push_rows(pv, fu(k, 0), fu(k, 1), sel_k, start, c.gu_off[k], first, count, false, &cnt.n, st));
             OF_CUDA(launch_peer_push_rows(pv, fv(k, 0), fv(k, 1), sel_k, start, c.gv_off[k], first, count, false, &cnt.n, st));
             if (world > 1) OF_CUDA(launch_peer_sync(pv, op++, &cnt.n, st));

@@ -38,9 +38,12 @@ struct PushArgs {
     size_t dst_off;       // byte offset of the gathered plane in every arena
     char* peer[PEER_MAX_WORLD];
     int world;
-    int skip;             // rank not to write to (-1: none): the source already is that rank's plane
-    size_t first;         // first element (row_a * W) and number of elements (rows * W) to push
+    size_t first;         // first element (row_a * W) and number of elements (rows * W) this rank owns
     size_t count;
+    // what each rank receives: elements [lo[r], hi[r]) of the plane, clipped to the owned range by the launcher
+    // (the whole owned range for an all-gather, the rows a neighbour's next stage reads for a halo push, empty
+    // for a rank that already holds the data)
+    size_t lo[PEER_MAX_WORLD], hi[PEER_MAX_WORLD];
 };
 
 __global__ void __launch_bounds__(256) push_rows_kernel(const PushArgs a) {
@@ -51,15 +54,27 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushArgs a) {
     const size_t n4 = vec ? a.count / 4 : 0;
     for (size_t i = tid; i < n4; i += stride) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        const size_t e = a.first + 4 * i;  // first of the four elements
 #pragma unroll
-        for (int r = 0; r < PEER_MAX_WORLD; ++r)
-            if (r < a.world && r != a.skip) reinterpret_cast<float4*>(a.peer[r] + a.dst_off + a.first * 4)[i] = v;
+        for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+            if (r >= a.world || e + 4 <= a.lo[r] || e >= a.hi[r]) continue;
+            float* d = reinterpret_cast<float*>(a.peer[r] + a.dst_off) + e;
+            if (e >= a.lo[r] && e + 4 <= a.hi[r]) {
+                *reinterpret_cast<float4*>(d) = v;
+            } else {  // a range that starts or ends inside this word
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (e + j >= a.lo[r] && e + j < a.hi[r]) d[j] = x[j];
+            }
+        }
     }
     for (size_t i = n4 * 4 + tid; i < a.count; i += stride) {
         const float v = __ldg(src + i);
+        const size_t e = a.first + i;
 #pragma unroll
         for (int r = 0; r < PEER_MAX_WORLD; ++r)
-            if (r < a.world && r != a.skip) reinterpret_cast<float*>(a.peer[r] + a.dst_off + a.first * 4)[i] = v;
+            if (r < a.world && e >= a.lo[r] && e < a.hi[r]) reinterpret_cast<float*>(a.peer[r] + a.dst_off)[e] = v;
     }
 }
 
@@ -139,9 +154,9 @@ void fill_peer_sync(PeerSync& s, const PeerView& pv, unsigned long long op) {
     s.timeout_ns = pv.timeout_ns;
 }
 
-cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
-                                  size_t dst_off, size_t first, size_t count, bool skip_self, int* launches,
-                                  cudaStream_t stream) {
+cudaError_t launch_peer_push_ranges(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
+                                    size_t dst_off, size_t first, size_t count, const size_t* lo, const size_t* hi,
+                                    int* launches, cudaStream_t stream) {
     if (count == 0) return cudaSuccess;
     PushArgs a;
     a.src[0] = src0;
@@ -149,17 +164,45 @@ cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const f
     a.sel = sel;
     a.sel_xor = sel_xor;
     a.dst_off = dst_off;
-    for (int r = 0; r < PEER_MAX_WORLD; ++r) a.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
     a.world = pv.world;
-    a.skip = skip_self ? pv.rank : -1;
     a.first = first;
     a.count = count;
-    size_t blocks = (count / 4 + 256 * 4 - 1) / (256 * 4);
+    size_t lo_min = first + count, hi_max = first;
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+        a.peer[r] = r < pv.world ? pv.peer[r] : nullptr;
+        size_t l = r < pv.world ? lo[r] : 0, h = r < pv.world ? hi[r] : 0;
+        if (l < first) l = first;
+        if (h > first + count) h = first + count;
+        if (h <= l) l = h = 0;
+        a.lo[r] = l;
+        a.hi[r] = h;
+        if (h > l) {
+            if (l < lo_min) lo_min = l;
+            if (h > hi_max) hi_max = h;
+        }
+    }
+    if (hi_max <= lo_min) return cudaSuccess;  // nobody needs anything of this rank's rows
+    // only the span somebody receives is read
+    a.first = lo_min;
+    a.count = hi_max - lo_min;
+    size_t blocks = (a.count / 4 + 256 * 4 - 1) / (256 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (launches) *launches += 1;
     OF_LAUNCH(push_rows_kernel, (unsigned)blocks, 256, 0, stream, a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_peer_push_rows(const PeerView& pv, const float* src0, const float* src1, const int* sel, int sel_xor,
+                                  size_t dst_off, size_t first, size_t count, bool skip_self, int* launches,
+                                  cudaStream_t stream) {
+    size_t lo[PEER_MAX_WORLD], hi[PEER_MAX_WORLD];
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+        const bool to = r < pv.world && !(skip_self && r == pv.rank);
+        lo[r] = to ? first : 0;
+        hi[r] = to ? first + count : 0;
+    }
+    return launch_peer_push_ranges(pv, src0, src1, sel, sel_xor, dst_off, first, count, lo, hi, launches, stream);
 }
 
 cudaError_t launch_peer_begin_run(const PeerView& pv, bool clear_error, int* launches, cudaStream_t stream) {

@@ -230,8 +230,10 @@ cudaError_t launch_pyramid_down(const float* src, float* dst, int batch, int H, 
         return e != nullptr && strcmp(e, "tile") == 0;
     }();
     static const int fast_flavour = [] {
-        const char* e = getenv("OF_B200_PYRAMID_FAST");  // f64: float64 + FMA (the former fast flavour), for A/B runs
-        return (e != nullptr && strcmp(e, "f64") == 0) ? 1 : 2;
+        // f32: the float32 flavour of the marching kernel (experiment: 2 x faster, but the per-pixel deviation of
+        // the fast pyramidal flow from the reference grows -- see DESIGN.md K2); default: float64 + FMA
+        const char* e = getenv("OF_B200_PYRAMID_FAST");
+        return (e != nullptr && strcmp(e, "f32") == 0) ? 2 : 1;
     }();
     if (!force_tile && pyramid_march_supported(H, W, oh, ow, radius))
         return launch_pyramid_march(src, dst, batch, H, W, oh, ow, weights, row_lo, row_hi, fast ? fast_flavour : 0, launches,

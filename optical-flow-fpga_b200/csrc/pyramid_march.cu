@@ -80,7 +80,7 @@ __device__ __forceinline__ double pm_gauss(const double* x, const double* w) {
     }
     return acc;
 }
-// float32 flavour (PM_F32, default of the fast pyramidal drivers): the same symmetric order with float32 fused
+// float32 flavour (PM_F32, an experiment behind OF_B200_PYRAMID_FAST=f32): the same symmetric order with float32 fused
 // multiply-adds -- no conversions, a quarter of the pipe time.  A smoothed value then carries a few float32
 // roundings (about 2 ulp, 3e-5 on a 0..255 image) instead of one.
 template <bool FMA>

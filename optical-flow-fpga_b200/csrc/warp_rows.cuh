@@ -32,17 +32,6 @@ __device__ __forceinline__ float warp_blend(const WarpTapT<F>& t) {
     return t.inside ? (float)acc : 0.0f;
 }
 
-// Fast mode (F = float): float32 lerps -- 3 FSUB + 3 FFMA instead of 7 conversions (quarter-rate pipe) and 14
-// float64 operations.  Exact when both fractions are 0 (integer flow, e.g. the zero flow every pyramid starts
-// from); otherwise within ~2 float32 ulp of the float64 blend.  Exact mode uses F = double (the blend above).
-template <>
-__device__ __forceinline__ float warp_blend<float>(const WarpTapT<float>& t) {
-    const float top = fmaf(t.fx, fsub(t.v01, t.v00), t.v00);
-    const float bot = fmaf(t.fx, fsub(t.v11, t.v10), t.v10);
-    const float r = fmaf(t.fy, fsub(bot, top), top);
-    return t.inside ? r : 0.0f;
-}
-
 // warp_image for the split refinement iteration: warped[y][x] = bilinear(curr, y + v, x + u) for
 // rows [row_lo, row_hi) of every pair that has not converged; 4 pixels per thread (128-bit flow
 // loads and stores, 16 gathers in flight).  Same arithmetic as the fused kernel's gather.

@@ -9,10 +9,11 @@
 
 using namespace ofb;
 
-// through the kernel's own launcher (grid, dynamic shared memory as on the device)
 template <int SRC>
 static void run(const TileArgs& a, int batch) {
-    launch_lk_tile5(SRC, a, batch, nullptr);
+    const int rows = (SRC == SRC_WARPED) ? a.row_hi - a.row_lo : a.H;
+    dim3 grid((a.W + T5_TX - 1) / T5_TX, (rows + T5_TY - 1) / T5_TY, batch);
+    cuda_on_host::launch(grid, T5_THREADS, [&a]() { lk_tile5_kernel<SRC>(a); });
 }
 
 extern "C" {

@@ -234,24 +234,20 @@ def test_warp_rows_double_source_on_cpu_is_warp_image(emul_warp, shape):
         assert np.array_equal(bits(got), bits(ref)), name
 
 
-def test_warp_rows_float_flavour_is_within_a_few_roundings(emul_warp):
-    """Fast flavour (float32 fractions, float32 lerps instead of the float64 blend): identical to warp_image when the
-    flow is integer (both fractions 0: the zero flow every pyramid starts from), within a few float32 roundings of a
-    0..255 sample otherwise, outside the frame exactly 0 (DESIGN.md K3 fast)."""
+def test_warp_rows_float_flavour_is_within_one_rounding(emul_warp):
+    """Fast flavour (float32 sample fractions): identical to warp_image for non-negative flow, a rounding of the
+    fraction away from it for negative flow (DESIGN.md K3 fast)."""
     rng = np.random.default_rng(4)
     shape = (40, 300)
     img = (rng.random(shape) * 255).astype(f32)
-    fu = np.rint(rng.standard_normal(shape) * 2).astype(f32)
-    fv = np.rint(rng.standard_normal(shape) * 2).astype(f32)
+    fu = np.abs(rng.standard_normal(shape) * 2).astype(f32)
+    fv = np.abs(rng.standard_normal(shape) * 2).astype(f32)
     assert np.array_equal(bits(run_warp(emul_warp, img, fu, fv, exact=False)), bits(orc.warp_image(img, fu, fv)))
-    for sign in (1.0, -1.0):
-        fu = (sign * np.abs(rng.standard_normal(shape) * 2)).astype(f32)
-        fv = (sign * np.abs(rng.standard_normal(shape) * 2)).astype(f32)
-        got, ref = run_warp(emul_warp, img, fu, fv, exact=False), orc.warp_image(img, fu, fv)
-        assert np.array_equal(got == 0.0, ref == 0.0)  # the same samples fall outside the frame
-        # three lerps on taps <= 255 apart, each within half an ulp of a value < 256, plus the float32 fraction
-        assert np.abs(got - ref).max() <= 4 * 255 * 2.0**-23
-        assert np.abs(got - ref).mean() < 2e-5
+    fu, fv = -fu, -fv
+    got, ref = run_warp(emul_warp, img, fu, fv, exact=False), orc.warp_image(img, fu, fv)
+    differ = bits(got) != bits(ref)
+    assert 0 < differ.mean() < 0.1
+    assert np.abs(got - ref).max() <= 255 * 2.0**-23  # the fraction moves by <= 2^-24, the taps are <= 255 apart
 
 
 def test_warp_rows_row_range(emul_warp):
@@ -388,11 +384,9 @@ def test_pyramid_march_batch_row_range_and_fma_flavour(emul_pyr):
     part = run_pyramid_down(emul_pyr, img, rows=(11, 37))  # row-band mode: only these coarse rows
     assert np.array_equal(bits(part[:, 11:37]), bits(want[:, 11:37]))
     assert np.isnan(part[:, :11]).all() and np.isnan(part[:, 37:]).all()
-    # fast mode: the float32 flavour (float32 fused multiply-adds per axis, float32 lerps): a few float32 roundings
-    # of a 0..255 value away from SciPy's bits, no bias
-    f32v = run_pyramid_down(emul_pyr, img, fast=True)
-    assert np.abs(f32v - want).max() <= 6 * np.spacing(f32(255.0))
-    assert abs(float((f32v.astype(np.float64) - want).mean())) < 2e-6
+    fma = run_pyramid_down(emul_pyr, img, fast=True)  # fast mode: fused multiply-adds, last-bit differences only
+    assert np.abs(fma - want).max() <= np.spacing(f32(255.0))
+    assert (bits(fma) != bits(want)).mean() < 1e-3
 
 
 def test_gradients_warp_upsample_launchers_source_on_cpu(emul_pyr):
