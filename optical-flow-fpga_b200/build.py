@@ -14,7 +14,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / os.environ.get("OF_B200_LIB_NAME", "libof_b200.so")  # variants: experiments only
-SOURCES = ["of_api.cu", "lk_march.cu", "lk_tile.cu", "lk_tile5.cu", "pyramid.cu", "pyramid_march.cu", "peer.cu", "metrics.cu", "motion.cu", "lk_fixed.cu"]
+SOURCES = ["of_api.cu", "lk_march.cu", "lk_tile.cu", "lk_tile5.cu", "lk_exact_march.cu", "pyramid.cu", "pyramid_march.cu", "peer.cu", "metrics.cu", "motion.cu", "lk_fixed.cu"]
 HEADERS = ["of_common.cuh", "f32x2.cuh", "of_kernels.h", "of_rowband.inl", "warp_rows.cuh", "../../include/of_b200.h"]
 
 NVCC_FLAGS = [

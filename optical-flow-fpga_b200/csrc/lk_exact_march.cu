@@ -1,0 +1,336 @@
+// K1 / K3 (exact), window 5, marching form: the reference's operation order (bit-identical on any float32
+// input, like lk_tile5.cu / lk_tile.cu) in a kernel that walks down the image instead of tiling it.
+//
+//   SRC_FRAMES  lucas_kanade_single_scale  (python/lucas_kanade_core.py:15-45, 48-70, 73-135)
+//   SRC_WARPED  one refinement iteration of lucas_kanade_pyramidal on (prev, warped curr): flow_out = flow_in + d
+//               and per-unit sums of |du|, |dv| (python/lucas_kanade_pyramidal.py:203-214)
+//
+// Why another kernel.  The tile kernels are issue-bound, and 40 % of what lk_tile5_kernel issues (100 of 265
+// lane-instructions per pixel, profiles/r01c) is not the arithmetic np.sum's order forces but tile overhead:
+// every 16 x 64 tile re-stages a 22 x 70 frame tile and re-derives a 20 x 68 product tile (1.5 / 1.33 pixels of
+// work per output), and every scalar float32 operation takes a full issue slot.  Here
+//   * a WARP owns two adjacent 58-column strips and marches down a band of rows, one frame row per step: every
+//     frame value is loaded, averaged and scaled once, every gradient and product formed once (the only
+//     redundancy is the 3-column halo of a strip, 6 / 64);
+//   * lane L holds columns 2L, 2L + 1 of BOTH strips, packed: one 64-bit word = the same column of strip A and
+//     strip B.  Every Sobel tap, product and window-sum addition is a Blackwell packed-pair instruction
+//     (FADD2 / FMUL2: one issue slot, two independent IEEE operations) on naturally aligned operands;
+//   * the rows in flight live in warp-private shared-memory rings (4 scaled-frame rows, 6 product rows), so a
+//     lane reads its neighbours' columns directly and the warp needs one __syncwarp() per step -- no block
+//     barrier, no shuffles.  The three stages of a step (stage frame row r, form the products of gradient row
+//     r - 2, finish output row r - 5) touch disjoint ring slots and overlap freely.
+// Per output the operations and their order are exactly lk_tile5_kernel's (scaled frame planes E = avg * 0.125,
+// D = avg * 0.25 so that a Sobel tap is one addition; zero taps contribute value * 0.0; the 25 products summed
+// like np.sum: 8 running lanes, tree, tail, + 0.0; Cramer without FMA), so the bits are the reference's.
+#include <cuda_runtime.h>
+
+#include "of_common.cuh"
+#include "f32x2.cuh"
+#include "of_kernels.h"
+
+namespace ofb {
+namespace {
+
+constexpr int XM_WARPS = 3;                 // units per CTA
+constexpr int XM_COLS = 64;                 // loaded columns per strip (2 per lane)
+constexpr int XM_OUT = XM_COLS - 6;         // 58 outputs per strip: Sobel 1 + window 2 columns of halo on both sides
+constexpr int XM_PAD = 2;                   // ring rows start 2 words in: word XM_PAD + j = local column j
+constexpr int XM_PITCH = XM_COLS + 4;       // words per ring row (one readable halo word on both sides, 16-byte rows)
+constexpr int XM_FRING = 4, XM_PRING = 6;   // ring depths: scaled-frame rows, product rows
+constexpr int XM_LAG_B = 2, XM_LAG_C = 5;   // a step stages frame row r, forms gradient row r - 2, emits output row r - 5
+constexpr int XM_EXTRA = 3 + XM_LAG_C;      // steps a band spends before its first / after its last output row
+constexpr int XM_WARP_WORDS = (3 * XM_FRING + 5 * XM_PRING) * XM_PITCH;
+constexpr size_t XM_SMEM_BYTES = (size_t)XM_WARPS * XM_WARP_WORDS * sizeof(f32x2);  // 68 544
+
+struct XmArgs {
+    TileArgs t;
+    int n_pairs_of_strips, n_bands, band_rows;
+    long long n_units;
+    int slots_per_pair;  // lk_tile_blocks_per_pair(rows, W): the partial-sum slots the iteration's tail reads
+};
+
+// np.sum's order as a streaming accumulator on packed pairs (see lk_tile5.cu)
+struct Np25x2 {
+    f32x2 lane[8];
+    f32x2 res;
+};
+__device__ __forceinline__ void np25_add(Np25x2& s, int t, f32x2 p) {
+    if (t < 8) {
+        s.lane[t] = p;
+    } else if (t < 24) {
+        s.lane[t & 7] = add2(s.lane[t & 7], p);
+    } else {
+        s.res = add2(add2(add2(s.lane[0], s.lane[1]), add2(s.lane[2], s.lane[3])),
+                     add2(add2(s.lane[4], s.lane[5]), add2(s.lane[6], s.lane[7])));
+        s.res = add2(s.res, p);
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const XmArgs xa) {
+    constexpr bool FLOW = (SRC == SRC_WARPED);
+    OF_DYNAMIC_SMEM_ALIGNED(16, unsigned char, xm_smem);
+    const TileArgs& a = xa.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long unit = (long long)blockIdx.x * XM_WARPS + warp;
+    if (unit >= xa.n_units) return;
+    const int sp = (int)(unit % xa.n_pairs_of_strips);
+    const long long rest = unit / xa.n_pairs_of_strips;
+    const int band = (int)(rest % xa.n_bands);
+    const int pair = (int)(rest / xa.n_bands);
+    if (FLOW && a.done != nullptr && a.done[pair]) return;  // level already converged
+
+    f32x2* ring = reinterpret_cast<f32x2*>(xm_smem) + (size_t)warp * XM_WARP_WORDS;
+    f32x2* sE = ring;                               // avg * 0.125  [XM_FRING][XM_PITCH], word = (strip A, strip B)
+    f32x2* sD = sE + XM_FRING * XM_PITCH;           // avg * 0.25
+    f32x2* sT = sD + XM_FRING * XM_PITCH;           // It = p - c
+    f32x2* prod = sT + XM_FRING * XM_PITCH;         // xx, yy, xy, xt, yt  [5][XM_PRING][XM_PITCH]
+
+    const int H = a.H, W = a.W;
+    const size_t plane = (size_t)H * W;
+    const int row_lo = FLOW ? a.row_lo : 0, row_hi = FLOW ? a.row_hi : H;
+    const int y0 = row_lo + band * xa.band_rows;
+    const int y1 = min(y0 + xa.band_rows, row_hi);
+    // image column of local column j: strip A (2 sp) starts at 58 * 2 sp - 3, strip B 58 columns further right
+    const int xA = XM_OUT * 2 * sp - 3 + 2 * lane, xB = xA + XM_OUT;
+    const float* __restrict__ gp = a.in0 + pair * plane;
+    const float* __restrict__ gc = a.in1 + pair * plane;
+    // replicated (= 'symm' for a 3 x 3 kernel) border: clamped coordinates
+    const int cA0 = clampi(xA, 0, W - 1), cA1 = clampi(xA + 1, 0, W - 1);
+    const int cB0 = clampi(xB, 0, W - 1), cB1 = clampi(xB + 1, 0, W - 1);
+
+    const float* fin_u = nullptr;
+    const float* fin_v = nullptr;
+    float* out_u;
+    float* out_v;
+    if (FLOW) {
+        const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
+        fin_u = (cur ? a.flow_u[1] : a.flow_u[0]) + pair * plane;
+        fin_v = (cur ? a.flow_v[1] : a.flow_v[0]) + pair * plane;
+        out_u = (cur ? a.flow_u[0] : a.flow_u[1]) + pair * plane;
+        out_v = (cur ? a.flow_v[0] : a.flow_v[1]) + pair * plane;
+    } else {
+        out_u = a.out_u + pair * plane;
+        out_v = a.out_v + pair * plane;
+    }
+    // which of this lane's four outputs per row exist: local columns 3 .. 60 of a strip, inside the frame
+    // (strip B of the last pair of strips may lie beyond it)
+    bool emit[2][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const bool local_ok = (2 * lane + k >= 3) && (2 * lane + k < 3 + XM_OUT);
+        emit[0][k] = local_ok && (xA + k < W);
+        emit[1][k] = local_ok && (xB + k < W);
+    }
+    const f32x2 zero2 = pk(0.0f, 0.0f), half2 = pk(0.5f, 0.5f), k125 = pk(0.125f, 0.125f), k25 = pk(0.25f, 0.25f);
+    const int wl = XM_PAD + 2 * lane;  // this lane's first word in a ring row
+    double acc_u = 0.0, acc_v = 0.0;
+
+    const int fr0 = y0 - 3;                       // first frame row staged
+    const int n_steps = (y1 - y0) + XM_EXTRA;
+    int pslot = 0;                                // product-ring slot of gradient row (fr - XM_LAG_B), advanced per step
+    for (int it = 0; it < n_steps; ++it) {
+        const int fr = fr0 + it;
+        // ---- stage A: frame row fr -> E, D, T (ring slot it & 3) -------------------------------------------------
+        if (fr <= y1 + 2) {
+            const size_t ro = (size_t)clampi(fr, 0, H - 1) * W;
+            const float pA0 = __ldg(gp + ro + cA0), pA1 = __ldg(gp + ro + cA1);
+            const float pB0 = __ldg(gp + ro + cB0), pB1 = __ldg(gp + ro + cB1);
+            const float qA0 = __ldg(gc + ro + cA0), qA1 = __ldg(gc + ro + cA1);
+            const float qB0 = __ldg(gc + ro + cB0), qB1 = __ldg(gc + ro + cB1);
+            const f32x2 p0 = pk(pA0, pB0), p1 = pk(pA1, pB1), c0 = pk(qA0, qB0), c1 = pk(qA1, qB1);
+            const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
+            const int w = (it & (XM_FRING - 1)) * XM_PITCH + wl;
+            *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
+            *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
+            *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
+        }
+        // ---- stage B: gradient row g = fr - 2 from frame rows g - 1, g, g + 1 (staged in earlier steps): Sobel in
+        // kernel order (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
+        if (it >= 3 && fr - XM_LAG_B <= y1 + 1) {
+            const f32x2* e_top = sE + ((it - 3) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g - 1, words wl - 1 .. wl + 2
+            const f32x2* e_bot = sE + ((it - 1) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g + 1
+            const f32x2* d_top = sD + ((it - 3) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
+            const f32x2* d_mid = sD + ((it - 2) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
+            const f32x2* d_bot = sD + ((it - 1) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
+            const f32x2* t_mid = sT + ((it - 2) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
+            f32x2 E0[4], E2[4], D1[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                E0[k] = e_top[k];
+                E2[k] = e_bot[k];
+                D1[k] = d_mid[k];
+            }
+            const f32x2 D0m[2] = {d_top[1], d_top[2]}, D2m[2] = {d_bot[1], d_bot[2]}, Tm[2] = {t_mid[1], t_mid[2]};
+            f32x2 pr[5][2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {  // this lane's two columns: taps at words c (left), c + 1, c + 2 (right)
+                // zero taps: value * 0.0f (keeps the reference's signed zeros / NaN propagation)
+                const f32x2 Z0 = mul2(D0m[c], zero2), Z2 = mul2(D2m[c], zero2);
+                const f32x2 Z1lo = mul2(D1[c], zero2), Z1m = mul2(D1[c + 1], zero2), Z1hi = mul2(D1[c + 2], zero2);
+                f32x2 ax = zero2, ay = zero2;
+                // j = 0 (frame row g + 1): kx = -.125, 0, .125   ky = -.125, -.25, -.125
+                ax = sub2(ax, E2[c + 2]);  ay = sub2(ay, E2[c + 2]);
+                ax = add2(ax, Z2);         ay = sub2(ay, D2m[c]);
+                ax = add2(ax, E2[c]);      ay = sub2(ay, E2[c]);
+                // j = 1 (frame row g): kx = -.25, 0, .25          ky = 0, 0, 0
+                ax = sub2(ax, D1[c + 2]);  ay = add2(ay, Z1hi);
+                ax = add2(ax, Z1m);        ay = add2(ay, Z1m);
+                ax = add2(ax, D1[c]);      ay = add2(ay, Z1lo);
+                // j = 2 (frame row g - 1): kx = -.125, 0, .125   ky = .125, .25, .125
+                ax = sub2(ax, E0[c + 2]);  ay = add2(ay, E0[c + 2]);
+                ax = add2(ax, Z0);         ay = add2(ay, D0m[c]);
+                ax = add2(ax, E0[c]);      ay = add2(ay, E0[c]);
+                pr[0][c] = mul2(ax, ax);
+                pr[1][c] = mul2(ay, ay);
+                pr[2][c] = mul2(ax, ay);
+                pr[3][c] = mul2(ax, Tm[c]);
+                pr[4][c] = mul2(ay, Tm[c]);
+            }
+            f32x2* pw = prod + pslot * XM_PITCH + wl;
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                *reinterpret_cast<ulonglong2*>(pw + q * (XM_PRING * XM_PITCH)) = make_ulonglong2(pr[q][0], pr[q][1]);
+        }
+        // ---- stage C: output row o = fr - 5 from product rows o - 2 .. o + 2 (slots pslot - 5 .. pslot - 1) -------
+        const int o = fr - XM_LAG_C;
+        if (o >= y0 && o < y1) {
+            f32x2 sum[5][2];
+            int rs[5];  // ring slots of product rows o - 2 + i
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                int s = pslot - 5 + i;
+                rs[i] = (s < 0 ? s + XM_PRING : s) * XM_PITCH + wl - 2;  // window of column j: words j - 2 .. j + 2
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const f32x2* P = prod + q * (XM_PRING * XM_PITCH);
+                Np25x2 s[2];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(P + rs[i]);
+                    const ulonglong2 q0 = row[0], q1 = row[1], q2 = row[2];
+                    const f32x2 v[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+#pragma unroll
+                    for (int w = 0; w < 2; ++w)
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) np25_add(s[w], 5 * i + k, v[w + k]);
+                }
+#pragma unroll
+                for (int w = 0; w < 2; ++w) sum[q][w] = add2(zero2, s[w].res);  // np.add.reduce starts from +0.0
+            }
+            const bool row_inside = (o >= 2 && o < H - 2);
+            const bool row_owned = FLOW && (o >= a.own_lo && o < a.own_hi);
+            const size_t ro = (size_t)o * W;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!emit[half][k]) continue;
+                    const int x = (half ? xB : xA) + k;
+                    float sq[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        float lo, hi;
+                        unpk(sum[q][k], lo, hi);
+                        sq[q] = half ? hi : lo;
+                    }
+                    float u, v;  // branch-free: the division runs on a safe denominator, the border / singular case selects 0
+                    cramer_solve_select(sq[0], sq[1], sq[2], sq[3], sq[4], row_inside && x >= 2 && x < W - 2, u, v);
+                    if (FLOW) {
+                        out_u[ro + x] = fadd(__ldg(fin_u + ro + x), u);  // flow += d
+                        out_v[ro + x] = fadd(__ldg(fin_v + ro + x), v);
+                        if (row_owned) {
+                            acc_u += (double)fabsf(u);
+                            acc_v += (double)fabsf(v);
+                        }
+                    } else {
+                        out_u[ro + x] = u;
+                        out_v[ro + x] = v;
+                    }
+                }
+            }
+        }
+        if (it >= 3) pslot = (pslot + 1 == XM_PRING) ? 0 : pslot + 1;
+        __syncwarp();
+    }
+
+    if (FLOW && a.partial != nullptr) {
+        // fixed shuffle tree over the warp; the unit's sums go to its slot, and the slots no unit owns (the tail of
+        // the iteration reads lk_tile_blocks_per_pair(rows, W) of them) are cleared by the units in turn
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc_u += __shfl_down_sync(0xffffffffu, acc_u, off);
+            acc_v += __shfl_down_sync(0xffffffffu, acc_v, off);
+        }
+        if (lane == 0) {
+            const int units_per_pair = xa.n_bands * xa.n_pairs_of_strips;
+            const int me = band * xa.n_pairs_of_strips + sp;
+            double* part = a.partial + (size_t)pair * xa.slots_per_pair * 2;
+            part[2 * me + 0] = acc_u;
+            part[2 * me + 1] = acc_v;
+            for (int s = me + units_per_pair; s < xa.slots_per_pair; s += units_per_pair) {
+                part[2 * s + 0] = 0.0;
+                part[2 * s + 1] = 0.0;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// window 5 on frames (single scale, or prev + the warped plane) for any frame size
+cudaError_t launch_lk_exact_march(int src, const TileArgs& a, int batch, cudaStream_t stream) {
+    if (batch < 1 || batch > 65535 || (size_t)a.H * a.W >= ((size_t)1 << 31)) return cudaErrorInvalidValue;
+    const int row_lo = (src == SRC_WARPED) ? a.row_lo : 0, row_hi = (src == SRC_WARPED) ? a.row_hi : a.H;
+    const int rows = row_hi - row_lo;
+    if (rows <= 0) return cudaErrorInvalidValue;
+    XmArgs x;
+    x.t = a;
+    const int n_strips = (a.W + XM_OUT - 1) / XM_OUT;
+    x.n_pairs_of_strips = (n_strips + 1) / 2;
+    x.slots_per_pair = lk_tile_blocks_per_pair(rows, a.W);
+    // Bands: units (one per warp) run in waves of 148 SMs x 9 resident warps and every band spends XM_EXTRA steps on
+    // warm-up; pick the band count that minimises  waves x (rows per band + XM_EXTRA).  Bands of at least 16 rows keep
+    // the units of a pair within the partial-sum slots (16 x 64 tiles) the iteration's tail reads.
+    const long long slots = 148LL * 3 * XM_WARPS;
+    const long long per_band = (long long)batch * x.n_pairs_of_strips;
+    const int max_bands = rows >= 32 ? rows / 16 : 1;
+    long long best_cost = -1;
+    int best_rows = rows;
+    for (int nb = 1; nb <= max_bands && nb <= 1024; ++nb) {
+        int br = (rows + nb - 1) / nb;
+        if (br < 16) br = 16;
+        const int bands = (rows + br - 1) / br;
+        const long long waves = (per_band * bands + slots - 1) / slots;
+        const long long cost = waves * (br + XM_EXTRA);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best_rows = br;
+        }
+    }
+    x.band_rows = best_rows;
+    x.n_bands = (rows + best_rows - 1) / best_rows;
+    x.n_units = (long long)batch * x.n_bands * x.n_pairs_of_strips;
+    if ((long long)x.n_bands * x.n_pairs_of_strips > x.slots_per_pair) return cudaErrorInvalidValue;  // cannot happen (see above)
+    const unsigned grid = (unsigned)((x.n_units + XM_WARPS - 1) / XM_WARPS);
+    static SmemOptIn opt_in[2];
+    switch (src) {
+        case SRC_FRAMES: {
+            const cudaError_t e = opt_in[0].ensure(lk_exact_march_kernel<SRC_FRAMES>, XM_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            OF_LAUNCH(lk_exact_march_kernel<SRC_FRAMES>, grid, XM_WARPS * 32, XM_SMEM_BYTES, stream, x);
+            break;
+        }
+        case SRC_WARPED: {
+            const cudaError_t e = opt_in[1].ensure(lk_exact_march_kernel<SRC_WARPED>, XM_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            OF_LAUNCH(lk_exact_march_kernel<SRC_WARPED>, grid, XM_WARPS * 32, XM_SMEM_BYTES, stream, x);
+            break;
+        }
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace ofb

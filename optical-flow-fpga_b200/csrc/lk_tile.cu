@@ -443,9 +443,21 @@ static bool tile_v2() {
     return v == 1;
 }
 
+// window 5 on frames: the marching form (lk_exact_march.cu) unless OF_B200_EXACT=tile (A/B runs).  Same bits.
+static bool exact_march() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OF_B200_EXACT");
+        v = (e && strcmp(e, "tile") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream) {
     if (batch > 65535) return cudaErrorInvalidValue;
     if (launches) *launches += 1;
+    if (window == 5 && (src == SRC_FRAMES || src == SRC_WARPED) && (size_t)a.H * a.W < ((size_t)1 << 31) && exact_march())
+        return launch_lk_exact_march(src, a, batch, stream);
     if (window == 5 && (src == SRC_FRAMES || src == SRC_WARPED) && (size_t)a.H * a.W < ((size_t)1 << 31) && tile_v2())
         return launch_lk_tile5(src, a, batch, stream);
     switch (src) {

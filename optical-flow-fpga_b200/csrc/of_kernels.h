@@ -166,6 +166,10 @@ struct TileArgs {
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream);
 // window 5, SRC_FRAMES / SRC_WARPED: second version of the kernel (lk_tile5.cu); called through launch_lk_tile
 cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t stream);
+// window 5, SRC_FRAMES / SRC_WARPED: the marching form of the exact kernel (lk_exact_march.cu; packed pairs, warp-private
+// shared-memory rings); called through launch_lk_tile.  Same bits; its per-unit partial sums fill the same
+// lk_tile_blocks_per_pair(rows, W) slots the tile kernels use.
+cudaError_t launch_lk_exact_march(int src, const TileArgs& a, int batch, cudaStream_t stream);
 int lk_tile_blocks_per_pair(int rows, int W);
 bool lk_tile_window_supported(int window);
 

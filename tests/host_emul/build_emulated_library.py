@@ -17,7 +17,7 @@ ROOT = HERE.parent.parent
 CSRC = ROOT / "optical-flow-fpga_b200" / "csrc"
 CUDA_INC = Path("/usr/local/cuda/include")
 OUT = HERE / "_build" / "libof_b200_emulated.so"
-UNITS = ["emul_of_api", "emul_lk_march", "emul_lk_tile", "emul_lk_tile5", "emul_pyramid", "emul_pyramid_march", "emul_motion",
+UNITS = ["emul_of_api", "emul_lk_march", "emul_lk_tile", "emul_lk_tile5", "emul_lk_exact_march", "emul_pyramid", "emul_pyramid_march", "emul_motion",
          "emul_fixed", "emul_metrics", "emul_peer", "fake_cudart"]
 
 
@@ -34,7 +34,7 @@ def build(force: bool = False) -> Path:
     for u in UNITS:
         obj = OUT.parent / f"{u}.o"
         cmd = [gxx, "-O1", "-ffp-contract=off", "-frounding-math", "-std=c++17", "-fPIC", "-pthread", "-w", "-DOF_HOST_EMULATION",
-               "-DCUDA_ON_HOST_FAKE_RUNTIME", "-I", str(CSRC), "-I", str(CUDA_INC), "-c", str(HERE / f"{u}.cpp"), "-o", str(obj)]
+               "-DCUDA_ON_HOST_FAKE_RUNTIME", "-DEMUL_EXACT_MARCH_NO_TILE_GEOMETRY", "-I", str(CSRC), "-I", str(CUDA_INC), "-c", str(HERE / f"{u}.cpp"), "-o", str(obj)]
         procs.append((u, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
         objs.append(str(obj))
     for u, p in procs:

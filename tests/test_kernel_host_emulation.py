@@ -35,30 +35,36 @@ f32 = np.float32
 _vp, _i = C.c_void_p, C.c_int
 
 
-def _build(tmp_path_factory, name, *more):
+def _build(tmp_path_factory, name, *more, defines=()):
     gxx = shutil.which("g++")
     if gxx is None or not (CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("needs g++ and the CUDA headers (vector types only; nothing CUDA is linked or run)")
     out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
     srcs = [str(ROOT / "tests" / "host_emul" / f"{n}.cpp") for n in (name,) + more]
     cmd = [gxx, "-O1", "-ffp-contract=off", "-frounding-math", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w",
-           "-DOF_HOST_EMULATION", "-I", str(CSRC), "-I", str(CUDA_INC), *srcs, "-o", str(out)]
+           "-DOF_HOST_EMULATION", *defines, "-I", str(CSRC), "-I", str(CUDA_INC), *srcs, "-o", str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     return C.CDLL(str(out))
 
 
-@pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    lib = _build(tmp_path_factory, "emul_lk_tile5")
-    lib.emul_lk_tile5_frames.argtypes = [_vp] * 4 + [_i] * 3
-    lib.emul_lk_tile5_warped.argtypes = [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
+@pytest.fixture(scope="module", params=["lk_exact_march", "lk_tile5"])
+def emul(tmp_path_factory, request):
+    """The two exact window-5 kernels behind the same two calls: lk_exact_march_kernel (the default; through its
+    launcher) and lk_tile5_kernel (OF_B200_EXACT=tile).  Every test that takes this fixture runs on both."""
+    name = request.param
+    lib = _build(tmp_path_factory, f"emul_{name}")
+    frames, warped = getattr(lib, f"emul_{name}_frames"), getattr(lib, f"emul_{name}_warped")
+    frames.argtypes = [_vp] * 4 + [_i] * 3
+    warped.argtypes = [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
+    lib.emul_lk_tile5_frames, lib.emul_lk_tile5_warped = frames, warped  # one spelling in the tests below
     return lib
 
 
 @pytest.fixture(scope="module")
 def emul_v1(tmp_path_factory):
-    lib = _build(tmp_path_factory, "emul_lk_tile", "emul_lk_tile5")  # launch_lk_tile dispatches to launch_lk_tile5
+    # launch_lk_tile dispatches to launch_lk_exact_march / launch_lk_tile5
+    lib = _build(tmp_path_factory, "emul_lk_tile", "emul_lk_tile5", "emul_lk_exact_march", defines=("-DEMUL_EXACT_MARCH_NO_TILE_GEOMETRY",))
     lib.emul_lk_tile.argtypes = [_i, _i] + [_vp] * 5 + [_i] * 3
     lib.emul_lk_tile_refine.argtypes = [_i, _i] + [_vp] * 6 + [_vp, _i, _vp, _vp] + [_i] * 7
     lib.emul_iter_finalize.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, C.c_long, _i, _i]
