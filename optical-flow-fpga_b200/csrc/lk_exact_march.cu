@@ -40,7 +40,7 @@ constexpr int XM_FRING = 4, XM_PRING = 6;   // ring depths: scaled-frame rows, p
 constexpr int XM_LAG_B = 2, XM_LAG_C = 5;   // a step stages frame row r, forms gradient row r - 2, emits output row r - 5
 constexpr int XM_EXTRA = 3 + XM_LAG_C;      // steps a band spends before its first / after its last output row
 constexpr int XM_WARP_WORDS = (3 * XM_FRING + 5 * XM_PRING) * XM_PITCH;
-constexpr size_t XM_SMEM_BYTES = (size_t)XM_WARPS * XM_WARP_WORDS * sizeof(f32x2);  // 68 544
+constexpr size_t XM_SMEM_BYTES = (size_t)XM_WARPS * XM_WARP_WORDS * sizeof(f32x2);  // 3 x 22 848
 
 struct XmArgs {
     TileArgs t;
@@ -81,6 +81,10 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
     if (FLOW && a.done != nullptr && a.done[pair]) return;  // level already converged
 
     f32x2* ring = reinterpret_cast<f32x2*>(xm_smem) + (size_t)warp * XM_WARP_WORDS;
+    // The scaled taps are formed in stage A and go through shared memory: ptxas fuses a packed mul.rn.f32x2 into a
+    // packed addition that consumes it (it honours .rn only for scalars; it also sees through fma(x, k, -0.0)), and an
+    // unrounded avg * k differs from the reference's rounded tap product when it is subnormal.  A store in between
+    // is the one thing it cannot fuse across.
     f32x2* sE = ring;                               // avg * 0.125  [XM_FRING][XM_PITCH], word = (strip A, strip B)
     f32x2* sD = sE + XM_FRING * XM_PITCH;           // avg * 0.25
     f32x2* sT = sD + XM_FRING * XM_PITCH;           // It = p - c
@@ -129,18 +133,38 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
     const int fr0 = y0 - 3;                       // first frame row staged
     const int n_steps = (y1 - y0) + XM_EXTRA;
     int pslot = 0;                                // product-ring slot of gradient row (fr - XM_LAG_B), advanced per step
+    // The eight frame values of a row are fetched one step ahead: a step's arithmetic (~800 instructions per lane)
+    // covers the latency, with nine warps per SM there is nobody else to hide it behind.
+    float nxt[8];
+    auto fetch_row = [&](int fr, float* dst) {
+        const size_t ro = (size_t)clampi(fr, 0, H - 1) * W;
+        dst[0] = __ldg(gp + ro + cA0);
+        dst[1] = __ldg(gp + ro + cA1);
+        dst[2] = __ldg(gp + ro + cB0);
+        dst[3] = __ldg(gp + ro + cB1);
+        dst[4] = __ldg(gc + ro + cA0);
+        dst[5] = __ldg(gc + ro + cA1);
+        dst[6] = __ldg(gc + ro + cB0);
+        dst[7] = __ldg(gc + ro + cB1);
+    };
+    fetch_row(fr0, nxt);
+    // output pointers of this lane's first column of either strip, advanced one row per emitted row
+    const size_t o_first = (size_t)y0 * W;
+    float* pu[2] = {out_u + o_first + xA, out_u + o_first + xB};
+    float* pv[2] = {out_v + o_first + xA, out_v + o_first + xB};
+    const float* qu[2] = {FLOW ? fin_u + o_first + xA : nullptr, FLOW ? fin_u + o_first + xB : nullptr};
+    const float* qv[2] = {FLOW ? fin_v + o_first + xA : nullptr, FLOW ? fin_v + o_first + xB : nullptr};
     for (int it = 0; it < n_steps; ++it) {
         const int fr = fr0 + it;
-        // ---- stage A: frame row fr -> E, D, T (ring slot it & 3) -------------------------------------------------
+        // ---- stage A: frame row fr -> E, D, T (ring slot it & 3); the next row's loads go out first ------------
         if (fr <= y1 + 2) {
-            const size_t ro = (size_t)clampi(fr, 0, H - 1) * W;
-            const float pA0 = __ldg(gp + ro + cA0), pA1 = __ldg(gp + ro + cA1);
-            const float pB0 = __ldg(gp + ro + cB0), pB1 = __ldg(gp + ro + cB1);
-            const float qA0 = __ldg(gc + ro + cA0), qA1 = __ldg(gc + ro + cA1);
-            const float qB0 = __ldg(gc + ro + cB0), qB1 = __ldg(gc + ro + cB1);
-            const f32x2 p0 = pk(pA0, pB0), p1 = pk(pA1, pB1), c0 = pk(qA0, qB0), c1 = pk(qA1, qB1);
-            const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
+            float cur[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+            if (fr + 1 <= y1 + 2) fetch_row(fr + 1, nxt);
+            const f32x2 p0 = pk(cur[0], cur[2]), p1 = pk(cur[1], cur[3]), c0 = pk(cur[4], cur[6]), c1 = pk(cur[5], cur[7]);
             const int w = (it & (XM_FRING - 1)) * XM_PITCH + wl;
+            const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
             *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
             *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
             *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
@@ -161,7 +185,8 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                 E2[k] = e_bot[k];
                 D1[k] = d_mid[k];
             }
-            const f32x2 D0m[2] = {d_top[1], d_top[2]}, D2m[2] = {d_bot[1], d_bot[2]}, Tm[2] = {t_mid[1], t_mid[2]};
+            const f32x2 D0m[2] = {d_top[1], d_top[2]}, D2m[2] = {d_bot[1], d_bot[2]};
+            const f32x2 Tm[2] = {t_mid[1], t_mid[2]};
             f32x2 pr[5][2];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {  // this lane's two columns: taps at words c (left), c + 1, c + 2 (right)
@@ -221,7 +246,6 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
             }
             const bool row_inside = (o >= 2 && o < H - 2);
             const bool row_owned = FLOW && (o >= a.own_lo && o < a.own_hi);
-            const size_t ro = (size_t)o * W;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -238,16 +262,25 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                     float u, v;  // branch-free: the division runs on a safe denominator, the border / singular case selects 0
                     cramer_solve_select(sq[0], sq[1], sq[2], sq[3], sq[4], row_inside && x >= 2 && x < W - 2, u, v);
                     if (FLOW) {
-                        out_u[ro + x] = fadd(__ldg(fin_u + ro + x), u);  // flow += d
-                        out_v[ro + x] = fadd(__ldg(fin_v + ro + x), v);
+                        pu[half][k] = fadd(__ldg(qu[half] + k), u);  // flow += d
+                        pv[half][k] = fadd(__ldg(qv[half] + k), v);
                         if (row_owned) {
                             acc_u += (double)fabsf(u);
                             acc_v += (double)fabsf(v);
                         }
                     } else {
-                        out_u[ro + x] = u;
-                        out_v[ro + x] = v;
+                        pu[half][k] = u;
+                        pv[half][k] = v;
                     }
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                pu[half] += W;
+                pv[half] += W;
+                if (FLOW) {
+                    qu[half] += W;
+                    qv[half] += W;
                 }
             }
         }

@@ -63,6 +63,30 @@ def test_argument_errors_come_before_any_device_work(of_b200):
         of_b200.lk_single_scale(np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4), np.float32))
 
 
+def test_caller_supplied_result_buffers_are_validated(of_b200):
+    """out=(u, v) of the batched calls reaches the C library as raw pointers: anything but two distinct writable
+    C-contiguous arrays of the batch's shape and float32 must be refused before the call."""
+    p = np.zeros((2, 16, 20), np.float32)
+    good = (np.empty_like(p), np.empty_like(p))
+    cases = {
+        "wrong dtype": (np.empty(p.shape, np.float64), good[1]),
+        "wrong shape": (np.empty((2, 16, 19), np.float32), good[1]),
+        "not contiguous": (np.empty((2, 16, 40), np.float32)[:, :, ::2], good[1]),
+        "same array twice": (good[0], good[0]),
+        "overlapping views": (np.empty((3, 16, 20), np.float32)[:2], None),
+        "read-only": (np.broadcast_to(np.float32(0), p.shape), good[1]),
+        "not a pair": (good[0],),
+    }
+    base = np.empty((3, 16, 20), np.float32)
+    cases["overlapping views"] = (base[:2], base[1:])
+    for name, out in cases.items():
+        for call in (lambda o: of_b200.lk_single_scale_batch(p, p, 5, of_b200.MODE_FAST, out=o),
+                     lambda o: of_b200.lk_pyramidal_batch(p, p, 2, 5, 2, of_b200.MODE_FAST, out=o),
+                     lambda o: of_b200.lk_single_scale_u8_batch(p.astype(np.uint8), p.astype(np.uint8), 5, of_b200.MODE_FAST, out=o)):
+            with pytest.raises(ValueError):
+                call(out)
+
+
 def test_no_cpu_fallback_without_a_device(of_b200):
     if of_b200.device_count() > 0:
         pytest.skip("a CUDA device is present")
