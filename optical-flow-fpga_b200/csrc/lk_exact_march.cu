@@ -133,21 +133,6 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
     const int fr0 = y0 - 3;                       // first frame row staged
     const int n_steps = (y1 - y0) + XM_EXTRA;
     int pslot = 0;                                // product-ring slot of gradient row (fr - XM_LAG_B), advanced per step
-    // The eight frame values of a row are fetched one step ahead: a step's arithmetic (~800 instructions per lane)
-    // covers the latency, with nine warps per SM there is nobody else to hide it behind.
-    float nxt[8];
-    auto fetch_row = [&](int fr, float* dst) {
-        const size_t ro = (size_t)clampi(fr, 0, H - 1) * W;
-        dst[0] = __ldg(gp + ro + cA0);
-        dst[1] = __ldg(gp + ro + cA1);
-        dst[2] = __ldg(gp + ro + cB0);
-        dst[3] = __ldg(gp + ro + cB1);
-        dst[4] = __ldg(gc + ro + cA0);
-        dst[5] = __ldg(gc + ro + cA1);
-        dst[6] = __ldg(gc + ro + cB0);
-        dst[7] = __ldg(gc + ro + cB1);
-    };
-    fetch_row(fr0, nxt);
     // output pointers of this lane's first column of either strip, advanced one row per emitted row
     const size_t o_first = (size_t)y0 * W;
     float* pu[2] = {out_u + o_first + xA, out_u + o_first + xB};
@@ -156,18 +141,24 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
     const float* qv[2] = {FLOW ? fin_v + o_first + xA : nullptr, FLOW ? fin_v + o_first + xB : nullptr};
     for (int it = 0; it < n_steps; ++it) {
         const int fr = fr0 + it;
-        // ---- stage A: frame row fr -> E, D, T (ring slot it & 3); the next row's loads go out first ------------
-        if (fr <= y1 + 2) {
-            float cur[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
-            if (fr + 1 <= y1 + 2) fetch_row(fr + 1, nxt);
-            const f32x2 p0 = pk(cur[0], cur[2]), p1 = pk(cur[1], cur[3]), c0 = pk(cur[4], cur[6]), c1 = pk(cur[5], cur[7]);
-            const int w = (it & (XM_FRING - 1)) * XM_PITCH + wl;
-            const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
-            *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
-            *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
-            *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
+        // ---- stage A, first half: the eight frame values of row fr.  They are consumed at the END of the step (the
+        // ring slot they go to is not read before the next step), so a whole step's arithmetic -- ~800 instructions
+        // per lane -- covers the latency; with nine warps per SM there is nobody else to hide it behind.
+        const bool stage_a = fr <= y1 + 2;
+        float fv8[8];
+        if (stage_a) {
+            // 32-bit element offsets (H * W < 2^31, launcher) and one widening multiply-add per address
+            const unsigned ro = (unsigned)clampi(fr, 0, H - 1) * (unsigned)W;
+            const char* bp = reinterpret_cast<const char*>(gp);
+            const char* bc = reinterpret_cast<const char*>(gc);
+            fv8[0] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA0) * 4u));
+            fv8[1] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA1) * 4u));
+            fv8[2] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cB0) * 4u));
+            fv8[3] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cB1) * 4u));
+            fv8[4] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cA0) * 4u));
+            fv8[5] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cA1) * 4u));
+            fv8[6] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB0) * 4u));
+            fv8[7] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB1) * 4u));
         }
         // ---- stage B: gradient row g = fr - 2 from frame rows g - 1, g, g + 1 (staged in earlier steps): Sobel in
         // kernel order (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
@@ -283,6 +274,15 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                     qv[half] += W;
                 }
             }
+        }
+        // ---- stage A, second half: frame row fr -> E, D, T (ring slot it & 3) -----------------------------------------
+        if (stage_a) {
+            const f32x2 p0 = pk(fv8[0], fv8[2]), p1 = pk(fv8[1], fv8[3]), c0 = pk(fv8[4], fv8[6]), c1 = pk(fv8[5], fv8[7]);
+            const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
+            const int w = (it & (XM_FRING - 1)) * XM_PITCH + wl;
+            *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
+            *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
+            *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
         }
         if (it >= 3) pslot = (pslot + 1 == XM_PRING) ? 0 : pslot + 1;
         __syncwarp();
