@@ -60,7 +60,7 @@ WORKLOADS = {
     "single_4k": dict(batch=64, H=2160, W=3840, pyramidal=False, levels=1, iters=1),
     # BASELINE config 5: few very large frames; with N > 1 GPUs every pair is split into row
     # bands over all ranks (strong scaling, all-reduce per iteration + all-gather per level in peer memory)
-    "pyramidal_8k": dict(batch=2, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True),
+    "pyramidal_8k": dict(batch=4, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True),
     "pyramidal_8k_exact": dict(batch=1, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True, variant="exact"),
 }
 # measured next to the primary workload by a default run (the `workloads` map of the JSON line)
@@ -443,13 +443,16 @@ def measure_e2e(env: Env, name: str, wl: dict, prev, curr, u, steps: int):
     torch, of_b200 = env.torch, env.ofb
     B, H, W = wl["batch"], wl["H"], wl["W"]
     variant = wl.get("variant")
-    u8 = variant == "u8"
+    fixed = variant == "fixed"
+    u8 = variant == "u8" or fixed
     eb = B
     bufs = None
     in_dtype = np.uint8 if u8 else np.float32
+    out_dtype = np.int16 if fixed else np.float32
     while eb >= 1:
         try:
-            bufs = [of_b200.PinnedArray((eb, H, W), in_dtype) for _ in range(2)] + [of_b200.PinnedArray((eb, H, W)) for _ in range(2)]
+            bufs = ([of_b200.PinnedArray((eb, H, W), in_dtype) for _ in range(2)] +
+                    [of_b200.PinnedArray((eb, H, W), out_dtype) for _ in range(2)])
             break
         except Exception:
             bufs = None
@@ -467,6 +470,11 @@ def measure_e2e(env: Env, name: str, wl: dict, prev, curr, u, steps: int):
 
         def call():
             of_b200.lk_pyramidal_batch(hp, hc, wl["levels"], WINDOW, wl["iters"], mode, out=(hu, hv))
+    elif fixed:
+        api = "of_lk_single_scale_fx (host buffers, pinned: uint8 frames in, int16 S8.7 flow out), chunked H2D/kernel/D2H on 3 streams"
+
+        def call():
+            of_b200.lk_single_scale_fx(hp, hc, True, out=(hu, hv))
     elif u8:
         api = "of_lk_single_scale_u8 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams"
 
@@ -487,9 +495,10 @@ def measure_e2e(env: Env, name: str, wl: dict, prev, curr, u, steps: int):
         call()
     torch.cuda.synchronize()
     e2e_ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
-    same = bool(np.array_equal(hu[eb - 1].view(np.uint32), u[eb - 1].cpu().numpy().view(np.uint32)))
+    dev_last = u[eb - 1].cpu().numpy()
+    same = bool(np.array_equal(hu[eb - 1], dev_last) if fixed else np.array_equal(hu[eb - 1].view(np.uint32), dev_last.view(np.uint32)))
     px = eb * H * W
-    h2d, d2h = 2 * px * (1 if u8 else 4), 2 * px * 4
+    h2d, d2h = 2 * px * (1 if u8 else 4), 2 * px * (2 if fixed else 4)
     out = {
         "value": env.world * px / (e2e_ms * 1e-3) / 1e6,
         "unit": "Mpixel/s",
@@ -569,10 +578,10 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
             # native driver: one C call per pair enqueues everything; the ranks meet through peer
             # memory inside the kernels.  The whole step is captured in a CUDA graph (the sequence
             # numbers of the collectives come from a device-side run counter, so replays are valid).
-            # Frame pairs of a step are independent: up to OF_B200_ROWBAND_LANES (default 2) of them are
+            # Frame pairs of a step are independent: up to OF_B200_ROWBAND_LANES (default 4) of them are
             # in flight at once, each on its own stream with its own arena, so the launch-latency-bound
-            # kernels of the coarse levels of one pair overlap with the other pair's.
-            n_lanes = max(1, min(B, int(os.environ.get("OF_B200_ROWBAND_LANES", "2"))))
+            # kernels of the coarse levels and the peer gathers of one pair overlap with the other pairs' work.
+            n_lanes = max(1, min(B, int(os.environ.get("OF_B200_ROWBAND_LANES", "4"))))
             lanes = ofd.PeerRowbandLanes(H, W, wl["levels"], WINDOW, wl["iters"], pyr_mode, lanes=n_lanes)
 
             def enqueue():
@@ -655,8 +664,8 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
 
     # ---- end to end through the host-buffer C ABI (pinned host arrays) ---------------------
     e2e = None
-    if want_e2e and not rowband and variant in (None, "u8", "exact") and not (wl["pyramidal"] and H * W > 3840 * 2160):
-        e2e = measure_e2e(env, name, wl, prev, curr, u, steps)
+    if want_e2e and not rowband and not (wl["pyramidal"] and H * W > 3840 * 2160):
+        e2e = measure_e2e(env, name, wl, prev, curr, u16 if variant == "fixed" else u, steps)
 
     if lanes is not None:
         lanes.close()

@@ -972,20 +972,35 @@ int of_lk_single_scale_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, 
     if (batch == 0) return OF_OK;
     OF_TRY(need_device());
     OF_HOST_PATH(hp);
-    const size_t n = (size_t)batch * height * width;
-    uint8_t *dp, *dc;
-    int16_t *du, *dv;
-    OF_TRY(hp->arena.get(0, n, reinterpret_cast<void**>(&dp)));
-    OF_TRY(hp->arena.get(1, n, reinterpret_cast<void**>(&dc)));
-    OF_TRY(hp->arena.get(2, n * 2, reinterpret_cast<void**>(&du)));
-    OF_TRY(hp->arena.get(3, n * 2, reinterpret_cast<void**>(&dv)));
-    cudaStream_t st = hp->streams[0];
-    OF_CUDA(cudaMemcpyAsync(dp, prev, n, cudaMemcpyHostToDevice, st));
-    OF_CUDA(cudaMemcpyAsync(dc, curr, n, cudaMemcpyHostToDevice, st));
-    OF_TRY(of_lk_single_scale_fx_dev(dp, dc, du, dv, batch, height, width, flags, st));
-    OF_CUDA(cudaMemcpyAsync(u, du, n * 2, cudaMemcpyDeviceToHost, st));
-    OF_CUDA(cudaMemcpyAsync(v, dv, n * 2, cudaMemcpyDeviceToHost, st));
-    OF_CUDA(cudaStreamSynchronize(st));
+    const size_t plane = (size_t)height * width;
+    // chunks of <= 64 MiB of flow per array, three in flight on three streams: H2D of chunk i+1 and D2H of chunk
+    // i-1 overlap the kernel of chunk i (pinned host memory needed for the copies to actually overlap)
+    size_t per_chunk = ((size_t)64 << 20) / (plane * sizeof(int16_t));
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > (size_t)batch) per_chunk = batch;
+    if (per_chunk > 65535) per_chunk = 65535;
+    const int n_chunks = (int)(((size_t)batch + per_chunk - 1) / per_chunk);
+    const int slots = n_chunks < HOST_STREAMS ? n_chunks : HOST_STREAMS;
+    uint8_t* d8[HOST_STREAMS][2];
+    int16_t* d16[HOST_STREAMS][2];
+    for (int s = 0; s < slots; ++s)
+        for (int j = 0; j < 2; ++j) {
+            OF_TRY(hp->arena.get(64 + (size_t)s * 4 + j, per_chunk * plane, reinterpret_cast<void**>(&d8[s][j])));
+            OF_TRY(hp->arena.get(64 + (size_t)s * 4 + 2 + j, per_chunk * plane * sizeof(int16_t), reinterpret_cast<void**>(&d16[s][j])));
+        }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % slots;
+        cudaStream_t st = hp->streams[s];
+        const size_t b0 = (size_t)c * per_chunk;
+        const int nb = (int)((size_t)batch - b0 < per_chunk ? (size_t)batch - b0 : per_chunk);
+        const size_t n = (size_t)nb * plane;
+        OF_CUDA(cudaMemcpyAsync(d8[s][0], prev + b0 * plane, n, cudaMemcpyHostToDevice, st));
+        OF_CUDA(cudaMemcpyAsync(d8[s][1], curr + b0 * plane, n, cudaMemcpyHostToDevice, st));
+        OF_TRY(of_lk_single_scale_fx_dev(d8[s][0], d8[s][1], d16[s][0], d16[s][1], nb, height, width, flags, st));
+        OF_CUDA(cudaMemcpyAsync(u + b0 * plane, d16[s][0], n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+        OF_CUDA(cudaMemcpyAsync(v + b0 * plane, d16[s][1], n * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < slots; ++s) OF_CUDA(cudaStreamSynchronize(hp->streams[s]));
     return OF_OK;
 }
 

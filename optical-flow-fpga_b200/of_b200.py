@@ -339,15 +339,16 @@ def lk_pyramidal(frame_prev, frame_curr, num_levels=3, window_size=5, num_iterat
     return res[0][0], res[1][0]
 
 
-def lk_single_scale_fx(prev_u8, curr_u8, mirror_avg_quirk: bool = True):
-    """uint8 frame pair(s) -> int16 S8.7 flow (value / 128 = pixels), RTL integer datapath."""
+def lk_single_scale_fx(prev_u8, curr_u8, mirror_avg_quirk: bool = True, out=None):
+    """uint8 frame pair(s) -> int16 S8.7 flow (value / 128 = pixels), RTL integer datapath.
+    out = (u, v): caller-supplied int16 result arrays of the frames' shape (e.g. pinned)."""
     p = np.ascontiguousarray(prev_u8, dtype=np.uint8)
     c = np.ascontiguousarray(curr_u8, dtype=np.uint8)
     if p.shape != c.shape or p.ndim not in (2, 3):
         raise ValueError("prev and curr must be uint8 arrays of equal shape, [H, W] or [B, H, W]")
     b = 1 if p.ndim == 2 else p.shape[0]
     h, w = p.shape[-2:]
-    u, v = np.empty(p.shape, np.int16), np.empty(p.shape, np.int16)
+    u, v = (np.empty(p.shape, np.int16), np.empty(p.shape, np.int16)) if out is None else _out_pair(out, p.shape, np.int16)
     flags = FX_MIRROR_AVG_QUIRK if mirror_avg_quirk else 0
     _check(lib().of_lk_single_scale_fx(_ptr(p), _ptr(c), _ptr(u), _ptr(v), b, h, w, flags))
     return u, v

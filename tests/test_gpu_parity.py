@@ -282,9 +282,10 @@ def test_pyramidal_other_presets_against_oracle(ofb, levels, iters, shape):
 
 
 def test_exact_mode_kernel_variants_give_the_same_bits(ofb):
-    """Exact mode has two switches, each read once per process, so every combination runs in a child:
+    """Exact mode has three switches, each read once per process, so every combination runs in a child:
     OF_B200_EXACT_REFINE = split (warp_rows_kernel<double> + tile kernel on (prev, warped)) | fused (the tile
-    kernel gathers its own halo), OF_B200_TILE = v1 (lk_tile_kernel) | v2 (lk_tile5_kernel, window 5).
+    kernel gathers its own halo), OF_B200_TILE = v1 (lk_tile_kernel) | v2 (lk_tile5_kernel, window 5),
+    OF_B200_EXACT = march (lk_exact_march_kernel: packed pairs, warp-private shared-memory rings) | tile.
     Single-scale on float frames (ragged shapes, one narrower than a tile) and a 3-level pyramidal run whose
     flow has both signs and leaves the frame (warp's outside -> 0 rule) must hash identically."""
     import os
@@ -309,11 +310,11 @@ def test_exact_mode_kernel_variants_give_the_same_bits(ofb):
         "print(h.hexdigest())\n"
     )
     got = {}
-    for refine, tile in (("fused", "v1"), ("split", "v1"), ("split", "v2")):
-        env = dict(os.environ, OF_B200_EXACT_REFINE=refine, OF_B200_TILE=tile)
+    for refine, tile, exact in (("fused", "v1", "tile"), ("split", "v1", "tile"), ("split", "v2", "tile"), ("split", "v2", "march")):
+        env = dict(os.environ, OF_B200_EXACT_REFINE=refine, OF_B200_TILE=tile, OF_B200_EXACT=exact)
         res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
         assert res.returncode == 0, res.stderr[-2000:]
-        got[(refine, tile)] = res.stdout.strip().splitlines()[-1]
+        got[(refine, tile, exact)] = res.stdout.strip().splitlines()[-1]
     assert len(set(got.values())) == 1, got
 
 
