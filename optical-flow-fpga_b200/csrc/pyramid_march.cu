@@ -169,11 +169,12 @@ __global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrM
             const int ybase = y_first + it * PM_CH;
 #pragma unroll
             for (int k = 0; k < PM_CH; ++k) x[2 * PM_R + k] = (A)nxt[k];
-            if (it + 1 < n_steps) {
+            // Unconditional: inside a branch the loads' destinations are copied into the loop-carried registers
+            // at the end of the block, and that copy waits for the loads (27 % of the kernel's stall samples,
+            // profiles/r02_pyrmarch_f32_experiment_*).  The last step re-reads the band's first rows instead.
+            const int nrow = (it + 1 < n_steps) ? ybase + PM_CH + PM_R : y_first;
 #pragma unroll
-                for (int k = 0; k < PM_CH; ++k)
-                    nxt[k] = __ldg(colp + (size_t)pm_reflect(ybase + PM_CH + PM_R + k, H) * W);
-            }
+            for (int k = 0; k < PM_CH; ++k) nxt[k] = __ldg(colp + (size_t)pm_reflect(nrow + k, H) * W);
             A* tw = tmp + (it & 1) * (PM_CH * PM_TPITCH) + tid;
 #pragma unroll
             for (int k = 0; k < PM_CH; ++k) tw[k * PM_TPITCH] = (A)(float)pm_gauss<FMA>(x + k, wt);
