@@ -41,7 +41,12 @@ typedef enum of_status {
 
 /* Arithmetic mode of the float path.
  * OF_MODE_EXACT  the reference's operation order (NumPy pairwise window sums, SciPy's
- *                float64 filters): bit-identical to the Python reference on any input.
+ *                float64 filters): every per-pixel operation is bit-identical to the Python reference on
+ *                any float32 input.  One reduction is not: the pyramidal path's early-exit test compares
+ *                mean|du|, mean|dv| of a level with 0.01, and those means are float64 sums rounded to
+ *                float32 here, float32 pairwise sums (np.mean) in the reference -- they agree to ~1e-7
+ *                relative, so an iteration count (and with it the flow) can differ only when a level's
+ *                mean residual lies within that distance of the threshold.
  * OF_MODE_FAST   separable window sums in registers (the throughput kernels); single scale:
  *                bit-identical to the reference on uint8-valued frames (all partial sums exactly
  *                representable), tolerance-level otherwise.  Pyramidal: additionally fused
