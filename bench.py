@@ -83,7 +83,7 @@ def hbm_peak():
 # DRAM bytes per launch of a workload's dominant kernel from the committed `ncu --set full` captures
 NCU_TRAFFIC = {
     # workload: (batch the capture was taken at, summary file)
-    "single_1080p": (256, "r01b_march_v2_ncu_full_summary.json"),
+    "single_1080p": (256, "r02_march_ncu_full_summary.json"),
 }
 
 
