@@ -786,6 +786,58 @@ def check_parity(env: Env, name, wl, prev, curr, u, v, fixed_out, rowband):
     return parity
 
 
+def verifier_patterns_report(of_b200):
+    """BASELINE configs[0-1] on the device: the 13 verifier patterns (committed fixtures under tests/golden/,
+    320 x 240) through both modes of both methods.  Per pattern: exact mode's largest metric deviation from the
+    reference's verification_baseline.json, and fast mode against exact mode per pixel (max |d| px, pixels
+    beyond 1e-3 px) -- the numbers the north star's tolerance (max |d| <= 1e-3 px, MAE / EPE equal to 3 decimals)
+    is about.  Exact mode is the conformant one; fast mode's per-pixel deviations are recorded, not hidden."""
+    golden = ROOT / "tests" / "golden"
+    try:
+        index = json.load(open(golden / "golden_index.json"))
+        frames = np.load(golden / "frames.npz")
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    names = list(index["patterns"])
+    prev = np.stack([frames[f"{n}__0"] for n in names]).astype(np.float32)
+    curr = np.stack([frames[f"{n}__1"] for n in names]).astype(np.float32)
+    h, w = prev.shape[1:]
+    out = {"shape": [int(h), int(w)], "pyramid": "3 levels x 3 iterations", "patterns": {}}
+    flows = {}
+    for method in ("single_scale", "pyramidal"):
+        for mode_name, mode in (("exact", of_b200.MODE_EXACT), ("fast", of_b200.MODE_FAST)):
+            if method == "single_scale":
+                flows[(method, mode_name)] = of_b200.lk_single_scale_batch(prev, curr, WINDOW, mode)
+            else:
+                flows[(method, mode_name)] = of_b200.lk_pyramidal_batch(prev, curr, 3, WINDOW, 3, mode)
+    worst = {"exact_metric_dev": 0.0, "fast_metric_dev": 0.0, "fast_max_abs_diff_px": 0.0, "fast_pixels_gt_1e-3": 0}
+    for i, n in enumerate(names):
+        e = index["patterns"][n]
+        region = of_b200.verifier_test_region((h, w), n, index["center_crop"])
+        entry = {}
+        for method in ("single_scale", "pyramidal"):
+            base = e["verification_baseline"][method]
+            rec = {}
+            for mode_name in ("exact", "fast"):
+                u, v = flows[(method, mode_name)]
+                m = of_b200.flow_metrics_batch(u[i], v[i], e["ground_truth"]["u"], e["ground_truth"]["v"], region)[0]
+                rec[f"{mode_name}_max_metric_dev_vs_baseline"] = max(abs(m[k] - base[k]) for k in of_b200.METRIC_NAMES)
+                rec[f"{mode_name}_mae_epe_equal_3_decimals"] = all(abs(m[k] - base[k]) < 5e-4 for k in ("mae_u", "mae_v", "epe"))
+            (ue, ve), (uf, vf) = flows[(method, "exact")], flows[(method, "fast")]
+            d = np.maximum(np.abs(uf[i] - ue[i]), np.abs(vf[i] - ve[i]))
+            rec["fast_vs_exact_max_abs_diff_px"] = float(d.max())
+            rec["fast_vs_exact_pixels_gt_1e-3"] = int((d > 1e-3).sum())
+            entry[method] = rec
+            worst["exact_metric_dev"] = max(worst["exact_metric_dev"], rec["exact_max_metric_dev_vs_baseline"])
+            worst["fast_metric_dev"] = max(worst["fast_metric_dev"], rec["fast_max_metric_dev_vs_baseline"])
+            worst["fast_max_abs_diff_px"] = max(worst["fast_max_abs_diff_px"], rec["fast_vs_exact_max_abs_diff_px"])
+            worst["fast_pixels_gt_1e-3"] = max(worst["fast_pixels_gt_1e-3"], rec["fast_vs_exact_pixels_gt_1e-3"])
+        out["patterns"][n] = entry
+    out["worst"] = worst
+    out["pixels_per_pattern"] = int(h * w)
+    return out
+
+
 def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     env = Env(args, rank, local_rank, world)
     primary = measure_workload(env, args.workload, wl, args.steps, args.warmup, want_e2e=not args.no_e2e)
@@ -812,6 +864,14 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
             "reference_literal_loop": {"what": "the reference's own per-pixel Python loop on one 320x240 pair, one core",
                                        "seconds": loop_s, "mpixel_per_s_one_core": loop_px / loop_s / 1e6},
         }
+
+    # ---- BASELINE configs[0-1]: the 13 verifier patterns, both methods, both modes (rank 0, N = 1) --------
+    verifier = None
+    if rank == 0 and world == 1 and args.workloads == "default" and args.workload == "single_1080p":
+        try:
+            verifier = verifier_patterns_report(env.ofb)
+        except Exception as e:
+            verifier = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- the other configurations, under the same clock -------------------------------------
     extra = {}
@@ -868,6 +928,8 @@ def gpu_arm(args, wl, rank: int, local_rank: int, world: int):
     }
     if extra:
         line["workloads"] = extra
+    if verifier is not None:
+        line["verifier_patterns"] = verifier
     print(json.dumps(line), flush=True)
 
 
