@@ -96,7 +96,14 @@ def test_pyramidal_fast_mode_13_patterns_within_tolerance(ofb, golden_index, gol
     """FAST pyramidal (register-marching refinement kernel): the warp blends in float64 with float32
     sample fractions (one rounding away from the reference's for negative flow), the window sums
     are separable float32.  Contract: MAE / EPE equal to the reference's to 3 decimals on every
-    verifier pattern; per-pixel deviations are confined to ill-conditioned pixels."""
+    verifier pattern and the same early-exit decisions; the per-pixel deviations are confined to ill-conditioned
+    pixels and are held to what was MEASURED per pattern (tests/golden/fast_mode_deviation.json,
+    written from bench.py's verifier_patterns report): no more pixels beyond 1e-3 px than recorded (+ 2 % slack
+    for a different summation order in a future kernel), no larger maximum than twice the recorded one.  Exact
+    mode is the one that meets the north star's per-pixel bound (it is bit-identical)."""
+    from conftest import GOLDEN
+
+    recorded = json.load(open(GOLDEN / "fast_mode_deviation.json"))["patterns"]
     report = {}
     for name, entry in golden_index["patterns"].items():
         p, c = (f.astype(np.float32) for f in golden_frames[name])
@@ -111,7 +118,9 @@ def test_pyramidal_fast_mode_13_patterns_within_tolerance(ofb, golden_index, gol
             assert abs(m[k] - entry["verification_baseline"]["pyramidal"][k]) < 5e-4, (name, k, m[k])
         d = np.maximum(np.abs(uf - ue), np.abs(vf - ve))
         report[name] = (float(d.max()), int((d > 1e-3).sum()))
-        assert (d > 1e-3).mean() < 0.05, (name, report[name])
+        rec = recorded[name]
+        assert report[name][1] <= rec["pixels_gt_1e-3"] * 1.02 + 8, (name, report[name], rec)
+        assert report[name][0] <= 2.0 * rec["max_abs_diff_px"] + 1e-6, (name, report[name], rec)
     print("fast-vs-exact pyramidal: max |d| px, pixels > 1e-3:", report)
     assert report["no_motion"] == (0.0, 0)
 
