@@ -70,14 +70,21 @@ __device__ __forceinline__ int pm_reflect(int i, int n) {
 // ~2^-52 of a float32 rounding boundary: about 5 values in 10^9 move by one float32 ulp.
 template <bool FMA>
 __device__ __forceinline__ double pm_gauss(const double* x, const double* w) {
+    if (FMA) {
+        // fast mode: two independent accumulators (even / odd pairs) halve the dependent chain of float64 FMAs the
+        // kernel waits on (its top stall is the fixed-latency dependency); one more addition, and the float64 sum
+        // is associated differently -- like the FMA itself, visible after the float32 store in ~1e-9 of the values
+        double a0 = dmul(x[PM_R], w[PM_R]), a1 = 0.0;
+#pragma unroll
+        for (int ii = -PM_R; ii < 0; ii += 2) {
+            a0 = fma(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R], a0);
+            a1 = fma(dadd(x[PM_R + ii + 1], x[PM_R - ii - 1]), w[ii + 1 + PM_R], a1);
+        }
+        return dadd(a0, a1);
+    }
     double acc = dmul(x[PM_R], w[PM_R]);
 #pragma unroll
-    for (int ii = -PM_R; ii < 0; ++ii) {
-        if (FMA)
-            acc = fma(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R], acc);
-        else
-            acc = dadd(acc, dmul(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R]));
-    }
+    for (int ii = -PM_R; ii < 0; ++ii) acc = dadd(acc, dmul(dadd(x[PM_R + ii], x[PM_R - ii]), w[ii + PM_R]));
     return acc;
 }
 // float32 flavour (PM_F32, an experiment behind OF_B200_PYRAMID_FAST=f32): the same symmetric order with float32 fused
