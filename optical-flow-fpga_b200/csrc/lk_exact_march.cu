@@ -16,9 +16,11 @@
 //     strip B.  Every Sobel tap, product and window-sum addition is a Blackwell packed-pair instruction
 //     (FADD2 / FMUL2: one issue slot, two independent IEEE operations) on naturally aligned operands;
 //   * the rows in flight live in warp-private shared-memory rings (4 scaled-frame rows, 6 product rows), so a
-//     lane reads its neighbours' columns directly and the warp needs one __syncwarp() per step -- no block
-//     barrier, no shuffles.  The three stages of a step (stage frame row r, form the products of gradient row
-//     r - 2, finish output row r - 5) touch disjoint ring slots and overlap freely.
+//     lane reads its neighbours' columns directly and the warp needs two __syncwarp() per step -- no block
+//     barrier, no shuffles;
+//   * a step handles TWO rows: with 23 KB of rings per warp only 9 warps fit an SM, so the latency has to be
+//     hidden inside the warp -- two output rows are two independent sets of accumulation chains, and they share
+//     every shared-memory load of the six product rows they read (3.75 instead of 6.25 128-bit loads per output).
 // Per output the operations and their order are exactly lk_tile5_kernel's (scaled frame planes E = avg * 0.125,
 // D = avg * 0.25 so that a Sobel tap is one addition; zero taps contribute value * 0.0; the 25 products summed
 // like np.sum: 8 running lanes, tree, tail, + 0.0; Cramer without FMA), so the bits are the reference's.
@@ -37,8 +39,7 @@ constexpr int XM_OUT = XM_COLS - 6;         // 58 outputs per strip: Sobel 1 + w
 constexpr int XM_PAD = 2;                   // ring rows start 2 words in: word XM_PAD + j = local column j
 constexpr int XM_PITCH = XM_COLS + 4;       // words per ring row (one readable halo word on both sides, 16-byte rows)
 constexpr int XM_FRING = 4, XM_PRING = 6;   // ring depths: scaled-frame rows, product rows
-constexpr int XM_LAG_B = 2, XM_LAG_C = 5;   // a step stages frame row r, forms gradient row r - 2, emits output row r - 5
-constexpr int XM_EXTRA = 3 + XM_LAG_C;      // steps a band spends before its first / after its last output row
+constexpr int XM_EXTRA = 8;                 // rows' worth of steps a band spends before its first output row (4 steps x 2 rows)
 constexpr int XM_WARP_WORDS = (3 * XM_FRING + 5 * XM_PRING) * XM_PITCH;
 constexpr size_t XM_SMEM_BYTES = (size_t)XM_WARPS * XM_WARP_WORDS * sizeof(f32x2);  // 3 x 22 848
 
@@ -130,161 +131,185 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
     const int wl = XM_PAD + 2 * lane;  // this lane's first word in a ring row
     double acc_u = 0.0, acc_v = 0.0;
 
-    const int fr0 = y0 - 3;                       // first frame row staged
-    const int n_steps = (y1 - y0) + XM_EXTRA;
-    int pslot = 0;                                // product-ring slot of gradient row (fr - XM_LAG_B), advanced per step
-    // output pointers of this lane's first column of either strip, advanced one row per emitted row
+    // Two rows per step.  Step `it` (frame rows fr = fr0 + 2 it and fr + 1):
+    //   1. the sixteen frame values of rows fr, fr + 1 are requested;
+    //   2. stage B forms the products of gradient rows g = fr - 3, g + 1 from frame rows fr - 4 .. fr - 1 (the four
+    //      ring slots, staged by earlier steps)                                                      __syncwarp()
+    //   3. stage C finishes output rows o = fr - 5, o + 1 from product rows o - 2 .. o + 3 (the six ring slots, the
+    //      last two written in 2.): the two rows share every shared-memory load and run as independent chains;
+    //   4. stage A turns the values of 1. into E, D, T rows fr, fr + 1 (over the slots of fr - 4, fr - 3, which 2.
+    //      has finished with)                                                                        __syncwarp()
+    const int fr0 = y0 - 3;                               // first frame row staged (gradient row y0 - 2 needs it)
+    const int n_steps = (y1 - y0 + 1) / 2 + 4;            // outputs start at step 4
+    int pslot = 0;                                        // product-ring slot of gradient row g of this step (0, 2, 4)
+    // output pointers of this lane's first column of either strip, advanced two rows per emitting step
     const size_t o_first = (size_t)y0 * W;
     float* pu[2] = {out_u + o_first + xA, out_u + o_first + xB};
     float* pv[2] = {out_v + o_first + xA, out_v + o_first + xB};
     const float* qu[2] = {FLOW ? fin_u + o_first + xA : nullptr, FLOW ? fin_u + o_first + xB : nullptr};
     const float* qv[2] = {FLOW ? fin_v + o_first + xA : nullptr, FLOW ? fin_v + o_first + xB : nullptr};
     for (int it = 0; it < n_steps; ++it) {
-        const int fr = fr0 + it;
-        // ---- stage A, first half: the eight frame values of row fr.  They are consumed at the END of the step (the
-        // ring slot they go to is not read before the next step), so a whole step's arithmetic -- ~800 instructions
-        // per lane -- covers the latency; with nine warps per SM there is nobody else to hide it behind.
-        const bool stage_a = fr <= y1 + 2;
-        float fv8[8];
-        if (stage_a) {
+        const int fr = fr0 + 2 * it;
+        // ---- 1. frame values of rows fr, fr + 1 (consumed in 4.: a whole step's arithmetic covers the latency)
+        float fv[2][8];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
             // 32-bit element offsets (H * W < 2^31, launcher) and one widening multiply-add per address
-            const unsigned ro = (unsigned)clampi(fr, 0, H - 1) * (unsigned)W;
+            const unsigned ro = (unsigned)clampi(fr + rr, 0, H - 1) * (unsigned)W;
             const char* bp = reinterpret_cast<const char*>(gp);
             const char* bc = reinterpret_cast<const char*>(gc);
-            fv8[0] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA0) * 4u));
-            fv8[1] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA1) * 4u));
-            fv8[2] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cB0) * 4u));
-            fv8[3] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cB1) * 4u));
-            fv8[4] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cA0) * 4u));
-            fv8[5] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cA1) * 4u));
-            fv8[6] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB0) * 4u));
-            fv8[7] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB1) * 4u));
+            fv[rr][0] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA0) * 4u));
+            fv[rr][1] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA1) * 4u));
+            fv[rr][2] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cB0) * 4u));
+            fv[rr][3] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cB1) * 4u));
+            fv[rr][4] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cA0) * 4u));
+            fv[rr][5] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cA1) * 4u));
+            fv[rr][6] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB0) * 4u));
+            fv[rr][7] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB1) * 4u));
         }
-        // ---- stage B: gradient row g = fr - 2 from frame rows g - 1, g, g + 1 (staged in earlier steps): Sobel in
-        // kernel order (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
-        if (it >= 3 && fr - XM_LAG_B <= y1 + 1) {
-            const f32x2* e_top = sE + ((it - 3) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g - 1, words wl - 1 .. wl + 2
-            const f32x2* e_bot = sE + ((it - 1) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g + 1
-            const f32x2* d_top = sD + ((it - 3) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
-            const f32x2* d_mid = sD + ((it - 2) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
-            const f32x2* d_bot = sD + ((it - 1) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
-            const f32x2* t_mid = sT + ((it - 2) & (XM_FRING - 1)) * XM_PITCH + wl - 1;
-            f32x2 E0[4], E2[4], D1[4];
+        // ---- 2. stage B: gradient rows g = fr - 3 and g + 1 from frame rows fr - 4 .. fr - 1: Sobel in kernel order
+        // (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
+        if (it >= 2) {
+            const int base = (2 * it) & (XM_FRING - 1);  // slot of frame row fr - 4 (rows fr + j sit in slot (2 it + j) & 3)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                E0[k] = e_top[k];
-                E2[k] = e_bot[k];
-                D1[k] = d_mid[k];
+            for (int rr = 0; rr < 2; ++rr) {
+                const int s_top = ((base + rr) & (XM_FRING - 1)) * XM_PITCH + wl - 1;      // frame row g - 1, words wl - 1 .. wl + 2
+                const int s_mid = ((base + rr + 1) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g
+                const int s_bot = ((base + rr + 2) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g + 1
+                f32x2 E0[4], E2[4], D1[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    E0[k] = sE[s_top + k];
+                    E2[k] = sE[s_bot + k];
+                    D1[k] = sD[s_mid + k];
+                }
+                const f32x2 D0m[2] = {sD[s_top + 1], sD[s_top + 2]}, D2m[2] = {sD[s_bot + 1], sD[s_bot + 2]};
+                const f32x2 Tm[2] = {sT[s_mid + 1], sT[s_mid + 2]};
+                f32x2 pr[5][2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {  // this lane's two columns: taps at words c (left), c + 1, c + 2 (right)
+                    // zero taps: value * 0.0f (keeps the reference's signed zeros / NaN propagation)
+                    const f32x2 Z0 = mul2(D0m[c], zero2), Z2 = mul2(D2m[c], zero2);
+                    const f32x2 Z1lo = mul2(D1[c], zero2), Z1m = mul2(D1[c + 1], zero2), Z1hi = mul2(D1[c + 2], zero2);
+                    f32x2 ax = zero2, ay = zero2;
+                    // j = 0 (frame row g + 1): kx = -.125, 0, .125   ky = -.125, -.25, -.125
+                    ax = sub2(ax, E2[c + 2]);  ay = sub2(ay, E2[c + 2]);
+                    ax = add2(ax, Z2);         ay = sub2(ay, D2m[c]);
+                    ax = add2(ax, E2[c]);      ay = sub2(ay, E2[c]);
+                    // j = 1 (frame row g): kx = -.25, 0, .25          ky = 0, 0, 0
+                    ax = sub2(ax, D1[c + 2]);  ay = add2(ay, Z1hi);
+                    ax = add2(ax, Z1m);        ay = add2(ay, Z1m);
+                    ax = add2(ax, D1[c]);      ay = add2(ay, Z1lo);
+                    // j = 2 (frame row g - 1): kx = -.125, 0, .125   ky = .125, .25, .125
+                    ax = sub2(ax, E0[c + 2]);  ay = add2(ay, E0[c + 2]);
+                    ax = add2(ax, Z0);         ay = add2(ay, D0m[c]);
+                    ax = add2(ax, E0[c]);      ay = add2(ay, E0[c]);
+                    pr[0][c] = mul2(ax, ax);
+                    pr[1][c] = mul2(ay, ay);
+                    pr[2][c] = mul2(ax, ay);
+                    pr[3][c] = mul2(ax, Tm[c]);
+                    pr[4][c] = mul2(ay, Tm[c]);
+                }
+                f32x2* pw = prod + (pslot + rr) * XM_PITCH + wl;
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    *reinterpret_cast<ulonglong2*>(pw + q * (XM_PRING * XM_PITCH)) = make_ulonglong2(pr[q][0], pr[q][1]);
             }
-            const f32x2 D0m[2] = {d_top[1], d_top[2]}, D2m[2] = {d_bot[1], d_bot[2]};
-            const f32x2 Tm[2] = {t_mid[1], t_mid[2]};
-            f32x2 pr[5][2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {  // this lane's two columns: taps at words c (left), c + 1, c + 2 (right)
-                // zero taps: value * 0.0f (keeps the reference's signed zeros / NaN propagation)
-                const f32x2 Z0 = mul2(D0m[c], zero2), Z2 = mul2(D2m[c], zero2);
-                const f32x2 Z1lo = mul2(D1[c], zero2), Z1m = mul2(D1[c + 1], zero2), Z1hi = mul2(D1[c + 2], zero2);
-                f32x2 ax = zero2, ay = zero2;
-                // j = 0 (frame row g + 1): kx = -.125, 0, .125   ky = -.125, -.25, -.125
-                ax = sub2(ax, E2[c + 2]);  ay = sub2(ay, E2[c + 2]);
-                ax = add2(ax, Z2);         ay = sub2(ay, D2m[c]);
-                ax = add2(ax, E2[c]);      ay = sub2(ay, E2[c]);
-                // j = 1 (frame row g): kx = -.25, 0, .25          ky = 0, 0, 0
-                ax = sub2(ax, D1[c + 2]);  ay = add2(ay, Z1hi);
-                ax = add2(ax, Z1m);        ay = add2(ay, Z1m);
-                ax = add2(ax, D1[c]);      ay = add2(ay, Z1lo);
-                // j = 2 (frame row g - 1): kx = -.125, 0, .125   ky = .125, .25, .125
-                ax = sub2(ax, E0[c + 2]);  ay = add2(ay, E0[c + 2]);
-                ax = add2(ax, Z0);         ay = add2(ay, D0m[c]);
-                ax = add2(ax, E0[c]);      ay = add2(ay, E0[c]);
-                pr[0][c] = mul2(ax, ax);
-                pr[1][c] = mul2(ay, ay);
-                pr[2][c] = mul2(ax, ay);
-                pr[3][c] = mul2(ax, Tm[c]);
-                pr[4][c] = mul2(ay, Tm[c]);
-            }
-            f32x2* pw = prod + pslot * XM_PITCH + wl;
-#pragma unroll
-            for (int q = 0; q < 5; ++q)
-                *reinterpret_cast<ulonglong2*>(pw + q * (XM_PRING * XM_PITCH)) = make_ulonglong2(pr[q][0], pr[q][1]);
         }
-        // ---- stage C: output row o = fr - 5 from product rows o - 2 .. o + 2 (slots pslot - 5 .. pslot - 1) -------
-        const int o = fr - XM_LAG_C;
-        if (o >= y0 && o < y1) {
-            f32x2 sum[5][2];
-            int rs[5];  // ring slots of product rows o - 2 + i
+        __syncwarp();
+        // ---- 3. stage C: output rows o = fr - 5 and o + 1 from product rows o - 2 .. o + 3 (slots pslot - 4 .. pslot + 1)
+        const int o = fr - 5;
+        if (it >= 4 && o < y1) {
+            const bool second = (o + 1 < y1);  // the band's last step may hold one row only
+            f32x2 sum[2][5][2];                // [row][quantity][column]
+            int rs[6];                         // ring offsets of product rows o - 2 + i
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                int s = pslot - 5 + i;
-                rs[i] = (s < 0 ? s + XM_PRING : s) * XM_PITCH + wl - 2;  // window of column j: words j - 2 .. j + 2
+            for (int i = 0; i < 6; ++i) {
+                int sl = pslot - 4 + i;
+                sl = sl < 0 ? sl + XM_PRING : (sl >= XM_PRING ? sl - XM_PRING : sl);
+                rs[i] = sl * XM_PITCH + wl - 2;  // window of column j: words j - 2 .. j + 2
             }
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 const f32x2* P = prod + q * (XM_PRING * XM_PITCH);
-                Np25x2 s[2];
+                Np25x2 s0[2], s1[2];  // windows of row o / row o + 1, this lane's two columns
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {
+                for (int i = 0; i < 6; ++i) {
                     const ulonglong2* row = reinterpret_cast<const ulonglong2*>(P + rs[i]);
                     const ulonglong2 q0 = row[0], q1 = row[1], q2 = row[2];
                     const f32x2 v[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
 #pragma unroll
                     for (int w = 0; w < 2; ++w)
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) np25_add(s[w], 5 * i + k, v[w + k]);
-                }
-#pragma unroll
-                for (int w = 0; w < 2; ++w) sum[q][w] = add2(zero2, s[w].res);  // np.add.reduce starts from +0.0
-            }
-            const bool row_inside = (o >= 2 && o < H - 2);
-            const bool row_owned = FLOW && (o >= a.own_lo && o < a.own_hi);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (!emit[half][k]) continue;
-                    const int x = (half ? xB : xA) + k;
-                    float sq[5];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        float lo, hi;
-                        unpk(sum[q][k], lo, hi);
-                        sq[q] = half ? hi : lo;
-                    }
-                    float u, v;  // branch-free: the division runs on a safe denominator, the border / singular case selects 0
-                    cramer_solve_select(sq[0], sq[1], sq[2], sq[3], sq[4], row_inside && x >= 2 && x < W - 2, u, v);
-                    if (FLOW) {
-                        pu[half][k] = fadd(__ldg(qu[half] + k), u);  // flow += d
-                        pv[half][k] = fadd(__ldg(qv[half] + k), v);
-                        if (row_owned) {
-                            acc_u += (double)fabsf(u);
-                            acc_v += (double)fabsf(v);
+                        for (int k = 0; k < 5; ++k) {
+                            if (i < 5) np25_add(s0[w], 5 * i + k, v[w + k]);
+                            if (i >= 1) np25_add(s1[w], 5 * (i - 1) + k, v[w + k]);
                         }
-                    } else {
-                        pu[half][k] = u;
-                        pv[half][k] = v;
+                }
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {  // np.add.reduce starts from +0.0
+                    sum[0][q][w] = add2(zero2, s0[w].res);
+                    sum[1][q][w] = add2(zero2, s1[w].res);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (rr == 1 && !second) break;
+                const int y = o + rr;
+                const bool row_inside = (y >= 2 && y < H - 2);
+                const bool row_owned = FLOW && (y >= a.own_lo && y < a.own_hi);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (!emit[half][k]) continue;
+                        const int x = (half ? xB : xA) + k;
+                        float sq[5];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            float lo, hi;
+                            unpk(sum[rr][q][k], lo, hi);
+                            sq[q] = half ? hi : lo;
+                        }
+                        float u, v;  // branch-free: the division runs on a safe denominator, the border / singular case selects 0
+                        cramer_solve_select(sq[0], sq[1], sq[2], sq[3], sq[4], row_inside && x >= 2 && x < W - 2, u, v);
+                        const size_t po = (size_t)rr * W + k;
+                        if (FLOW) {
+                            pu[half][po] = fadd(__ldg(qu[half] + po), u);  // flow += d
+                            pv[half][po] = fadd(__ldg(qv[half] + po), v);
+                            if (row_owned) {
+                                acc_u += (double)fabsf(u);
+                                acc_v += (double)fabsf(v);
+                            }
+                        } else {
+                            pu[half][po] = u;
+                            pv[half][po] = v;
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                pu[half] += W;
-                pv[half] += W;
+                pu[half] += 2 * (size_t)W;
+                pv[half] += 2 * (size_t)W;
                 if (FLOW) {
-                    qu[half] += W;
-                    qv[half] += W;
+                    qu[half] += 2 * (size_t)W;
+                    qv[half] += 2 * (size_t)W;
                 }
             }
         }
-        // ---- stage A, second half: frame row fr -> E, D, T (ring slot it & 3) -----------------------------------------
-        if (stage_a) {
-            const f32x2 p0 = pk(fv8[0], fv8[2]), p1 = pk(fv8[1], fv8[3]), c0 = pk(fv8[4], fv8[6]), c1 = pk(fv8[5], fv8[7]);
+        // ---- 4. stage A: frame rows fr, fr + 1 -> E, D, T (ring slots (2 it) & 3, (2 it + 1) & 3)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const f32x2 p0 = pk(fv[rr][0], fv[rr][2]), p1 = pk(fv[rr][1], fv[rr][3]);
+            const f32x2 c0 = pk(fv[rr][4], fv[rr][6]), c1 = pk(fv[rr][5], fv[rr][7]);
             const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
-            const int w = (it & (XM_FRING - 1)) * XM_PITCH + wl;
+            const int w = ((2 * it + rr) & (XM_FRING - 1)) * XM_PITCH + wl;
             *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
             *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
             *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
         }
-        if (it >= 3) pslot = (pslot + 1 == XM_PRING) ? 0 : pslot + 1;
+        if (it >= 2) pslot = (pslot + 2 >= XM_PRING) ? pslot + 2 - XM_PRING : pslot + 2;
         __syncwarp();
     }
 
