@@ -167,6 +167,24 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
             fv[rr][6] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB0) * 4u));
             fv[rr][7] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB1) * 4u));
         }
+        // the flow the step's two output rows are added to (refinement iteration): requested now, used at the end of 3.
+        const int o = fr - 5;
+        const bool emit_rows = (it >= 4 && o < y1);
+        const bool second = (o + 1 < y1);  // the band's last step may hold one row only
+        float fin[2][2][2][2];             // [row][half][column][u, v]
+        if (FLOW && emit_rows) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const bool live = emit[half][k] && (rr == 0 || second);
+                        const size_t po = (size_t)rr * W + k;
+                        fin[rr][half][k][0] = live ? __ldg(qu[half] + po) : 0.0f;
+                        fin[rr][half][k][1] = live ? __ldg(qv[half] + po) : 0.0f;
+                    }
+        }
         // ---- 2. stage B: gradient rows g = fr - 3 and g + 1 from frame rows fr - 4 .. fr - 1: Sobel in kernel order
         // (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
         if (it >= 2) {
@@ -218,9 +236,7 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
         }
         __syncwarp();
         // ---- 3. stage C: output rows o = fr - 5 and o + 1 from product rows o - 2 .. o + 3 (slots pslot - 4 .. pslot + 1)
-        const int o = fr - 5;
-        if (it >= 4 && o < y1) {
-            const bool second = (o + 1 < y1);  // the band's last step may hold one row only
+        if (emit_rows) {
             f32x2 sum[2][5][2];                // [row][quantity][column]
             int rs[6];                         // ring offsets of product rows o - 2 + i
 #pragma unroll
@@ -275,8 +291,8 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                         cramer_solve_select(sq[0], sq[1], sq[2], sq[3], sq[4], row_inside && x >= 2 && x < W - 2, u, v);
                         const size_t po = (size_t)rr * W + k;
                         if (FLOW) {
-                            pu[half][po] = fadd(__ldg(qu[half] + po), u);  // flow += d
-                            pv[half][po] = fadd(__ldg(qv[half] + po), v);
+                            pu[half][po] = fadd(fin[rr][half][k][0], u);  // flow += d
+                            pv[half][po] = fadd(fin[rr][half][k][1], v);
                             if (row_owned) {
                                 acc_u += (double)fabsf(u);
                                 acc_v += (double)fabsf(v);
