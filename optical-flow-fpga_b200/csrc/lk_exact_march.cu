@@ -191,18 +191,27 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
             const int base = (2 * it) & (XM_FRING - 1);  // slot of frame row fr - 4 (rows fr + j sit in slot (2 it + j) & 3)
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-                const int s_top = ((base + rr) & (XM_FRING - 1)) * XM_PITCH + wl - 1;      // frame row g - 1, words wl - 1 .. wl + 2
-                const int s_mid = ((base + rr + 1) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g
-                const int s_bot = ((base + rr + 2) & (XM_FRING - 1)) * XM_PITCH + wl - 1;  // frame row g + 1
+                // 128-bit loads of aligned word pairs (conflict-free at the lanes' 16-byte stride): words wl - 2 .. wl + 3
+                // of the top / middle / bottom rows, of which wl - 1 .. wl + 2 are the taps of this lane's two columns
+                const int s_top = ((base + rr) & (XM_FRING - 1)) * XM_PITCH + wl - 2;      // frame row g - 1
+                const int s_mid = ((base + rr + 1) & (XM_FRING - 1)) * XM_PITCH + wl - 2;  // frame row g
+                const int s_bot = ((base + rr + 2) & (XM_FRING - 1)) * XM_PITCH + wl - 2;  // frame row g + 1
+                auto load4 = [](const f32x2* row, f32x2* dst) {  // words 1 .. 4 of the six at `row`
+                    const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(row);
+                    const ulonglong2 a0 = r2[0], a1 = r2[1], a2 = r2[2];
+                    dst[0] = a0.y;
+                    dst[1] = a1.x;
+                    dst[2] = a1.y;
+                    dst[3] = a2.x;
+                };
                 f32x2 E0[4], E2[4], D1[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    E0[k] = sE[s_top + k];
-                    E2[k] = sE[s_bot + k];
-                    D1[k] = sD[s_mid + k];
-                }
-                const f32x2 D0m[2] = {sD[s_top + 1], sD[s_top + 2]}, D2m[2] = {sD[s_bot + 1], sD[s_bot + 2]};
-                const f32x2 Tm[2] = {sT[s_mid + 1], sT[s_mid + 2]};
+                load4(sE + s_top, E0);
+                load4(sE + s_bot, E2);
+                load4(sD + s_mid, D1);
+                const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(sD + s_top + 2);
+                const ulonglong2 d2 = *reinterpret_cast<const ulonglong2*>(sD + s_bot + 2);
+                const ulonglong2 t1 = *reinterpret_cast<const ulonglong2*>(sT + s_mid + 2);
+                const f32x2 D0m[2] = {d0.x, d0.y}, D2m[2] = {d2.x, d2.y}, Tm[2] = {t1.x, t1.y};
                 f32x2 pr[5][2];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {  // this lane's two columns: taps at words c (left), c + 1, c + 2 (right)
@@ -275,20 +284,28 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                 const bool row_inside = (y >= 2 && y < H - 2);
                 const bool row_owned = FLOW && (y >= a.own_lo && y < a.own_hi);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int k = 0; k < 2; ++k) {
+                    // Cramer's determinants for both strips at once (lucas_kanade_core.py:122-133; b0 = -sxt, b1 = -syt and
+                    // negation commutes with rounding): every product rounds on its own, then the difference.  Written as
+                    // fma(c * d, -1, a * b): ptxas would fuse a packed multiply into a packed subtraction.
+                    const f32x2 m1 = pk(-1.0f, -1.0f);
+                    const f32x2 sxx = sum[rr][0][k], syy = sum[rr][1][k], sxy = sum[rr][2][k], sxt = sum[rr][3][k], syt = sum[rr][4][k];
+                    const f32x2 det2 = fma2(mul2(sxy, sxy), m1, mul2(sxx, syy));
+                    const f32x2 nu2 = fma2(mul2(syy, sxt), m1, mul2(sxy, syt));
+                    const f32x2 nv2 = fma2(mul2(sxx, syt), m1, mul2(sxy, sxt));
+                    float det[2], nu[2], nv[2];
+                    unpk(det2, det[0], det[1]);
+                    unpk(nu2, nu[0], nu[1]);
+                    unpk(nv2, nv[0], nv[1]);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
+                    for (int half = 0; half < 2; ++half) {
                         if (!emit[half][k]) continue;
                         const int x = (half ? xB : xA) + k;
-                        float sq[5];
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            float lo, hi;
-                            unpk(sum[rr][q][k], lo, hi);
-                            sq[q] = half ? hi : lo;
-                        }
-                        float u, v;  // branch-free: the division runs on a safe denominator, the border / singular case selects 0
-                        cramer_solve_select(sq[0], sq[1], sq[2], sq[3], sq[4], row_inside && x >= 2 && x < W - 2, u, v);
+                        // branch-free: the division runs on a safe denominator, the border / singular case selects 0
+                        const bool ok = row_inside && x >= 2 && x < W - 2 && (fabsf(det[half]) > OF_DET_EPS);
+                        const float den = ok ? det[half] : 1.0f;
+                        const float qu_ = fdiv(nu[half], den), qv_ = fdiv(nv[half], den);
+                        const float u = ok ? qu_ : 0.0f, v = ok ? qv_ : 0.0f;
                         const size_t po = (size_t)rr * W + k;
                         if (FLOW) {
                             pu[half][po] = fadd(fin[rr][half][k][0], u);  // flow += d

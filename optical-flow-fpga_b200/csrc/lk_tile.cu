@@ -443,15 +443,13 @@ static bool tile_v2() {
     return v == 1;
 }
 
-// window 5 on frames: OF_B200_EXACT=march selects the marching form (lk_exact_march.cu).  Same bits as the tile kernel
-// (GPU suite green with it as the default), fewer instructions per pixel (196 against 265), but at 8 - 9 resident warps
-// per SM (22.8 KB of warp-private shared memory each) it is latency-bound and slower: 1.94 ms against 1.55 ms for
-// 64 x 1080p (profiles/r02_exact_march_*).  It stays selectable for A/B runs.
+// window 5 on frames: the marching form (lk_exact_march.cu: packed pairs, warp-private shared-memory rings, two rows per
+// step) unless OF_B200_EXACT=tile selects the tile kernel (A/B runs).  Same bits.
 static bool exact_march() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("OF_B200_EXACT");
-        v = (e && strcmp(e, "march") == 0) ? 1 : 0;
+        v = (e && strcmp(e, "tile") == 0) ? 0 : 1;
     }
     return v == 1;
 }
