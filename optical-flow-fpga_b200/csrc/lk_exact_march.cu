@@ -33,15 +33,17 @@
 namespace ofb {
 namespace {
 
-constexpr int XM_WARPS = 3;                 // units per CTA
+constexpr int XM_WARPS = 2;                 // a unit (= CTA) is two warps that share one set of rings
 constexpr int XM_COLS = 64;                 // loaded columns per strip (2 per lane)
 constexpr int XM_OUT = XM_COLS - 6;         // 58 outputs per strip: Sobel 1 + window 2 columns of halo on both sides
 constexpr int XM_PAD = 2;                   // ring rows start 2 words in: word XM_PAD + j = local column j
 constexpr int XM_PITCH = XM_COLS + 4;       // words per ring row (one readable halo word on both sides, 16-byte rows)
-constexpr int XM_FRING = 4, XM_PRING = 6;   // ring depths: scaled-frame rows, product rows
-constexpr int XM_EXTRA = 8;                 // rows' worth of steps a band spends before its first output row (4 steps x 2 rows)
-constexpr int XM_WARP_WORDS = (3 * XM_FRING + 5 * XM_PRING) * XM_PITCH;
-constexpr size_t XM_SMEM_BYTES = (size_t)XM_WARPS * XM_WARP_WORDS * sizeof(f32x2);  // 3 x 22 848
+constexpr int XM_FRING = 8, XM_PRING = 8;   // ring depths (powers of two): scaled-frame rows, product rows
+constexpr int XM_STEP = 2 * XM_WARPS;       // rows per step: two per warp
+constexpr int XM_EXTRA = 12;                // rows' worth of steps a band spends before its first output row (3 steps x 4 rows)
+constexpr int XM_UNIT_WORDS = (3 * XM_FRING + 5 * XM_PRING) * XM_PITCH;
+constexpr size_t XM_SMEM_BYTES = (size_t)XM_UNIT_WORDS * sizeof(f32x2);  // 34 816
+constexpr int XM_UNITS_PER_SM = 6;          // 209 KB of shared memory, 12 warps, <= 170 registers per thread
 
 struct XmArgs {
     TileArgs t;
@@ -68,20 +70,19 @@ __device__ __forceinline__ void np25_add(Np25x2& s, int t, f32x2 p) {
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const XmArgs xa) {
+__global__ void __launch_bounds__(XM_WARPS * 32, XM_UNITS_PER_SM) lk_exact_march_kernel(const XmArgs xa) {
     constexpr bool FLOW = (SRC == SRC_WARPED);
     OF_DYNAMIC_SMEM_ALIGNED(16, unsigned char, xm_smem);
     const TileArgs& a = xa.t;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long unit = (long long)blockIdx.x * XM_WARPS + warp;
-    if (unit >= xa.n_units) return;
+    const long long unit = blockIdx.x;  // one unit per CTA: everything below up to the row loop is CTA-uniform
     const int sp = (int)(unit % xa.n_pairs_of_strips);
     const long long rest = unit / xa.n_pairs_of_strips;
     const int band = (int)(rest % xa.n_bands);
     const int pair = (int)(rest / xa.n_bands);
     if (FLOW && a.done != nullptr && a.done[pair]) return;  // level already converged
 
-    f32x2* ring = reinterpret_cast<f32x2*>(xm_smem) + (size_t)warp * XM_WARP_WORDS;
+    f32x2* ring = reinterpret_cast<f32x2*>(xm_smem);
     // The scaled taps are formed in stage A and go through shared memory: ptxas fuses a packed mul.rn.f32x2 into a
     // packed addition that consumes it (it honours .rn only for scalars; it also sees through fma(x, k, -0.0)), and an
     // unrounded avg * k differs from the reference's rounded tap product when it is subnormal.  A store in between
@@ -131,31 +132,31 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
     const int wl = XM_PAD + 2 * lane;  // this lane's first word in a ring row
     double acc_u = 0.0, acc_v = 0.0;
 
-    // Two rows per step.  Step `it` (frame rows fr = fr0 + 2 it and fr + 1):
-    //   1. the sixteen frame values of rows fr, fr + 1 are requested;
-    //   2. stage B forms the products of gradient rows g = fr - 3, g + 1 from frame rows fr - 4 .. fr - 1 (the four
-    //      ring slots, staged by earlier steps)                                                      __syncwarp()
-    //   3. stage C finishes output rows o = fr - 5, o + 1 from product rows o - 2 .. o + 3 (the six ring slots, the
-    //      last two written in 2.): the two rows share every shared-memory load and run as independent chains;
-    //   4. stage A turns the values of 1. into E, D, T rows fr, fr + 1 (over the slots of fr - 4, fr - 3, which 2.
-    //      has finished with)                                                                        __syncwarp()
-    const int fr0 = y0 - 3;                               // first frame row staged (gradient row y0 - 2 needs it)
-    const int n_steps = (y1 - y0 + 1) / 2 + 4;            // outputs start at step 4
-    int pslot = 0;                                        // product-ring slot of gradient row g of this step (0, 2, 4)
-    // output pointers of this lane's first column of either strip, advanced two rows per emitting step
-    const size_t o_first = (size_t)y0 * W;
+    // Four rows per step, two per warp.  Step `it` (frame rows fr .. fr + 3, fr = fr0 + 4 it); warp w takes rows 2 w, 2 w + 1
+    // of every stage:
+    //   1. the frame values of its rows fr + 2 w, fr + 2 w + 1 are requested;
+    //   2. stage B forms the products of its gradient rows g + 2 w, g + 2 w + 1 (g = fr - 5) from frame rows staged by
+    //      earlier steps                                                                               __syncthreads()
+    //   3. stage C finishes its output rows o + 2 w, o + 2 w + 1 (o = fr - 7) from six product rows (the newest written
+    //      in 2. by either warp): the two rows share every shared-memory load and run as independent chains;
+    //   4. stage A turns the values of 1. into E, D, T rows (over ring slots 2. has finished with)  __syncthreads()
+    // Frame row fr0 + j lives in ring slot j & 7, the product row of gradient row y0 - 2 + p in slot p & 7.
+    const int fr0 = y0 - 5;
+    const int n_steps = (y1 - y0 + XM_STEP - 1) / XM_STEP + 3;  // outputs start at step 3
+    // output pointers of this lane's first column of either strip at this warp's first row, advanced per emitting step
+    const size_t o_first = (size_t)(y0 + 2 * warp) * W;
     float* pu[2] = {out_u + o_first + xA, out_u + o_first + xB};
     float* pv[2] = {out_v + o_first + xA, out_v + o_first + xB};
     const float* qu[2] = {FLOW ? fin_u + o_first + xA : nullptr, FLOW ? fin_u + o_first + xB : nullptr};
     const float* qv[2] = {FLOW ? fin_v + o_first + xA : nullptr, FLOW ? fin_v + o_first + xB : nullptr};
     for (int it = 0; it < n_steps; ++it) {
-        const int fr = fr0 + 2 * it;
-        // ---- 1. frame values of rows fr, fr + 1 (consumed in 4.: a whole step's arithmetic covers the latency)
+        const int jw = XM_STEP * it + 2 * warp;  // ring index of this warp's first frame row of the step
+        // ---- 1. frame values of this warp's two rows (consumed in 4.: a whole step's arithmetic covers the latency)
         float fv[2][8];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             // 32-bit element offsets (H * W < 2^31, launcher) and one widening multiply-add per address
-            const unsigned ro = (unsigned)clampi(fr + rr, 0, H - 1) * (unsigned)W;
+            const unsigned ro = (unsigned)clampi(fr0 + jw + rr, 0, H - 1) * (unsigned)W;
             const char* bp = reinterpret_cast<const char*>(gp);
             const char* bc = reinterpret_cast<const char*>(gc);
             fv[rr][0] = __ldg(reinterpret_cast<const float*>(bp + (size_t)(ro + (unsigned)cA0) * 4u));
@@ -167,10 +168,10 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
             fv[rr][6] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB0) * 4u));
             fv[rr][7] = __ldg(reinterpret_cast<const float*>(bc + (size_t)(ro + (unsigned)cB1) * 4u));
         }
-        // the flow the step's two output rows are added to (refinement iteration): requested now, used at the end of 3.
-        const int o = fr - 5;
-        const bool emit_rows = (it >= 4 && o < y1);
-        const bool second = (o + 1 < y1);  // the band's last step may hold one row only
+        // the flow this warp's two output rows are added to (refinement iteration): requested now, used at the end of 3.
+        const int o = y0 + XM_STEP * (it - 3) + 2 * warp;  // this warp's first output row of the step
+        const bool emit_rows = (it >= 3 && o < y1);
+        const bool second = (o + 1 < y1);  // the band may end on this warp's first row
         float fin[2][2][2][2];             // [row][half][column][u, v]
         if (FLOW && emit_rows) {
 #pragma unroll
@@ -185,17 +186,17 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                         fin[rr][half][k][1] = live ? __ldg(qv[half] + po) : 0.0f;
                     }
         }
-        // ---- 2. stage B: gradient rows g = fr - 3 and g + 1 from frame rows fr - 4 .. fr - 1: Sobel in kernel order
-        // (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
+        // ---- 2. stage B: this warp's gradient rows (ring indices jw - 5, jw - 4) from frame rows jw - 6 .. jw - 3: Sobel
+        // in kernel order (j, k) -- tap (j, k) reads frame offset (1 - j, 1 - k) from the centre -- and the five products
         if (it >= 2) {
-            const int base = (2 * it) & (XM_FRING - 1);  // slot of frame row fr - 4 (rows fr + j sit in slot (2 it + j) & 3)
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 // 128-bit loads of aligned word pairs (conflict-free at the lanes' 16-byte stride): words wl - 2 .. wl + 3
                 // of the top / middle / bottom rows, of which wl - 1 .. wl + 2 are the taps of this lane's two columns
-                const int s_top = ((base + rr) & (XM_FRING - 1)) * XM_PITCH + wl - 2;      // frame row g - 1
-                const int s_mid = ((base + rr + 1) & (XM_FRING - 1)) * XM_PITCH + wl - 2;  // frame row g
-                const int s_bot = ((base + rr + 2) & (XM_FRING - 1)) * XM_PITCH + wl - 2;  // frame row g + 1
+                const int jg = jw - 5 + rr;  // ring index of the gradient row's own frame row
+                const int s_top = ((jg - 1) & (XM_FRING - 1)) * XM_PITCH + wl - 2;
+                const int s_mid = (jg & (XM_FRING - 1)) * XM_PITCH + wl - 2;
+                const int s_bot = ((jg + 1) & (XM_FRING - 1)) * XM_PITCH + wl - 2;
                 auto load4 = [](const f32x2* row, f32x2* dst) {  // words 1 .. 4 of the six at `row`
                     const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(row);
                     const ulonglong2 a0 = r2[0], a1 = r2[1], a2 = r2[2];
@@ -237,23 +238,20 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                     pr[3][c] = mul2(ax, Tm[c]);
                     pr[4][c] = mul2(ay, Tm[c]);
                 }
-                f32x2* pw = prod + (pslot + rr) * XM_PITCH + wl;
+                // gradient row y0 - 2 + p with p = jw - 8 + rr (jg = jw - 5 + rr is frame row y0 - 5 + jg)
+                f32x2* pw = prod + ((jw - 8 + rr) & (XM_PRING - 1)) * XM_PITCH + wl;
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                     *reinterpret_cast<ulonglong2*>(pw + q * (XM_PRING * XM_PITCH)) = make_ulonglong2(pr[q][0], pr[q][1]);
             }
         }
-        __syncwarp();
-        // ---- 3. stage C: output rows o = fr - 5 and o + 1 from product rows o - 2 .. o + 3 (slots pslot - 4 .. pslot + 1)
+        __syncthreads();
+        // ---- 3. stage C: this warp's output rows o, o + 1 from product rows o - 2 .. o + 3 (indices jw - 12 .. jw - 7)
         if (emit_rows) {
             f32x2 sum[2][5][2];                // [row][quantity][column]
             int rs[6];                         // ring offsets of product rows o - 2 + i
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                int sl = pslot - 4 + i;
-                sl = sl < 0 ? sl + XM_PRING : (sl >= XM_PRING ? sl - XM_PRING : sl);
-                rs[i] = sl * XM_PITCH + wl - 2;  // window of column j: words j - 2 .. j + 2
-            }
+            for (int i = 0; i < 6; ++i) rs[i] = ((jw - 12 + i) & (XM_PRING - 1)) * XM_PITCH + wl - 2;  // window of column j: words j - 2 .. j + 2
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 const f32x2* P = prod + q * (XM_PRING * XM_PITCH);
@@ -321,48 +319,55 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 3) lk_exact_march_kernel(const 
                     }
                 }
             }
+        }
+        if (it >= 3) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                pu[half] += 2 * (size_t)W;
-                pv[half] += 2 * (size_t)W;
+                pu[half] += XM_STEP * (size_t)W;
+                pv[half] += XM_STEP * (size_t)W;
                 if (FLOW) {
-                    qu[half] += 2 * (size_t)W;
-                    qv[half] += 2 * (size_t)W;
+                    qu[half] += XM_STEP * (size_t)W;
+                    qv[half] += XM_STEP * (size_t)W;
                 }
             }
         }
-        // ---- 4. stage A: frame rows fr, fr + 1 -> E, D, T (ring slots (2 it) & 3, (2 it + 1) & 3)
+        // ---- 4. stage A: this warp's frame rows -> E, D, T (ring slots jw & 7, (jw + 1) & 7)
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const f32x2 p0 = pk(fv[rr][0], fv[rr][2]), p1 = pk(fv[rr][1], fv[rr][3]);
             const f32x2 c0 = pk(fv[rr][4], fv[rr][6]), c1 = pk(fv[rr][5], fv[rr][7]);
             const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
-            const int w = ((2 * it + rr) & (XM_FRING - 1)) * XM_PITCH + wl;
+            const int w = ((jw + rr) & (XM_FRING - 1)) * XM_PITCH + wl;
             *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
             *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
             *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
         }
-        if (it >= 2) pslot = (pslot + 2 >= XM_PRING) ? pslot + 2 - XM_PRING : pslot + 2;
-        __syncwarp();
+        __syncthreads();
     }
 
     if (FLOW && a.partial != nullptr) {
-        // fixed shuffle tree over the warp; the unit's sums go to its slot, and the slots no unit owns (the tail of
-        // the iteration reads lk_tile_blocks_per_pair(rows, W) of them) are cleared by the units in turn
+        // fixed shuffle tree over each warp, then warp 0 + warp 1; the unit's sums go to its slot, and the slots no unit
+        // owns (the tail of the iteration reads lk_tile_blocks_per_pair(rows, W) of them) are cleared by the units in turn
+        __shared__ double red[2][XM_WARPS];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             acc_u += __shfl_down_sync(0xffffffffu, acc_u, off);
             acc_v += __shfl_down_sync(0xffffffffu, acc_v, off);
         }
         if (lane == 0) {
+            red[0][warp] = acc_u;
+            red[1][warp] = acc_v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
             const int units_per_pair = xa.n_bands * xa.n_pairs_of_strips;
             const int me = band * xa.n_pairs_of_strips + sp;
             double* part = a.partial + (size_t)pair * xa.slots_per_pair * 2;
-            part[2 * me + 0] = acc_u;
-            part[2 * me + 1] = acc_v;
-            for (int s = me + units_per_pair; s < xa.slots_per_pair; s += units_per_pair) {
-                part[2 * s + 0] = 0.0;
-                part[2 * s + 1] = 0.0;
+            part[2 * me + 0] = red[0][0] + red[0][1];
+            part[2 * me + 1] = red[1][0] + red[1][1];
+            for (int s_ = me + units_per_pair; s_ < xa.slots_per_pair; s_ += units_per_pair) {
+                part[2 * s_ + 0] = 0.0;
+                part[2 * s_ + 1] = 0.0;
             }
         }
     }
@@ -381,10 +386,10 @@ cudaError_t launch_lk_exact_march(int src, const TileArgs& a, int batch, cudaStr
     const int n_strips = (a.W + XM_OUT - 1) / XM_OUT;
     x.n_pairs_of_strips = (n_strips + 1) / 2;
     x.slots_per_pair = lk_tile_blocks_per_pair(rows, a.W);
-    // Bands: units (one per warp) run in waves of 148 SMs x 9 resident warps and every band spends XM_EXTRA steps on
+    // Bands: units (one per CTA of two warps) run in waves of 148 SMs x 6 resident units and every band spends XM_EXTRA rows on
     // warm-up; pick the band count that minimises  waves x (rows per band + XM_EXTRA).  Bands of at least 16 rows keep
     // the units of a pair within the partial-sum slots (16 x 64 tiles) the iteration's tail reads.
-    const long long slots = 148LL * 3 * XM_WARPS;
+    const long long slots = 148LL * XM_UNITS_PER_SM;
     const long long per_band = (long long)batch * x.n_pairs_of_strips;
     const int max_bands = rows >= 32 ? rows / 16 : 1;
     long long best_cost = -1;
@@ -404,7 +409,8 @@ cudaError_t launch_lk_exact_march(int src, const TileArgs& a, int batch, cudaStr
     x.n_bands = (rows + best_rows - 1) / best_rows;
     x.n_units = (long long)batch * x.n_bands * x.n_pairs_of_strips;
     if ((long long)x.n_bands * x.n_pairs_of_strips > x.slots_per_pair) return cudaErrorInvalidValue;  // cannot happen (see above)
-    const unsigned grid = (unsigned)((x.n_units + XM_WARPS - 1) / XM_WARPS);
+    if (x.n_units > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)x.n_units;  // one unit per CTA
     static SmemOptIn opt_in[2];
     switch (src) {
         case SRC_FRAMES: {
