@@ -38,12 +38,12 @@ constexpr int XM_COLS = 64;                 // loaded columns per strip (2 per l
 constexpr int XM_OUT = XM_COLS - 6;         // 58 outputs per strip: Sobel 1 + window 2 columns of halo on both sides
 constexpr int XM_PAD = 2;                   // ring rows start 2 words in: word XM_PAD + j = local column j
 constexpr int XM_PITCH = XM_COLS + 4;       // words per ring row (one readable halo word on both sides, 16-byte rows)
-constexpr int XM_FRING = 6, XM_PRING = 8;   // ring depths: scaled-frame rows (the minimum: slot = index % 6), product rows
+constexpr int XM_FRING = 8, XM_PRING = 8;   // ring depths (powers of two): scaled-frame rows, product rows
 constexpr int XM_STEP = 2 * XM_WARPS;       // rows per step: two per warp
 constexpr int XM_EXTRA = 12;                // rows' worth of steps a band spends before its first output row (3 steps x 4 rows)
 constexpr int XM_UNIT_WORDS = (3 * XM_FRING + 5 * XM_PRING) * XM_PITCH;
-constexpr size_t XM_SMEM_BYTES = (size_t)XM_UNIT_WORDS * sizeof(f32x2);  // 31 552
-constexpr int XM_UNITS_PER_SM = 7;          // 221 KB of shared memory, 14 warps, 128 registers per thread
+constexpr size_t XM_SMEM_BYTES = (size_t)XM_UNIT_WORDS * sizeof(f32x2);  // 34 816
+constexpr int XM_UNITS_PER_SM = 6;          // 209 KB of shared memory, 12 warps, <= 170 registers per thread
 
 struct XmArgs {
     TileArgs t;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(XM_WARPS * 32, XM_UNITS_PER_SM) lk_exact_march
     //   3. stage C finishes its output rows o + 2 w, o + 2 w + 1 (o = fr - 7) from six product rows (the newest written
     //      in 2. by either warp): the two rows share every shared-memory load and run as independent chains;
     //   4. stage A turns the values of 1. into E, D, T rows (over ring slots 2. has finished with)  __syncthreads()
-    // Frame row fr0 + j lives in ring slot j % 6, the product row of gradient row y0 - 2 + p in slot p & 7.
+    // Frame row fr0 + j lives in ring slot j & 7, the product row of gradient row y0 - 2 + p in slot p & 7.
     const int fr0 = y0 - 5;
     const int n_steps = (y1 - y0 + XM_STEP - 1) / XM_STEP + 3;  // outputs start at step 3
     // output pointers of this lane's first column of either strip at this warp's first row, advanced per emitting step
@@ -194,9 +194,9 @@ __global__ void __launch_bounds__(XM_WARPS * 32, XM_UNITS_PER_SM) lk_exact_march
                 // 128-bit loads of aligned word pairs (conflict-free at the lanes' 16-byte stride): words wl - 2 .. wl + 3
                 // of the top / middle / bottom rows, of which wl - 1 .. wl + 2 are the taps of this lane's two columns
                 const int jg = jw - 5 + rr;  // ring index of the gradient row's own frame row
-                const int s_top = (int)((unsigned)(jg - 1) % XM_FRING) * XM_PITCH + wl - 2;
-                const int s_mid = (int)((unsigned)jg % XM_FRING) * XM_PITCH + wl - 2;
-                const int s_bot = (int)((unsigned)(jg + 1) % XM_FRING) * XM_PITCH + wl - 2;
+                const int s_top = ((jg - 1) & (XM_FRING - 1)) * XM_PITCH + wl - 2;
+                const int s_mid = (jg & (XM_FRING - 1)) * XM_PITCH + wl - 2;
+                const int s_bot = ((jg + 1) & (XM_FRING - 1)) * XM_PITCH + wl - 2;
                 auto load4 = [](const f32x2* row, f32x2* dst) {  // words 1 .. 4 of the six at `row`
                     const ulonglong2* r2 = reinterpret_cast<const ulonglong2*>(row);
                     const ulonglong2 a0 = r2[0], a1 = r2[1], a2 = r2[2];
@@ -331,13 +331,13 @@ __global__ void __launch_bounds__(XM_WARPS * 32, XM_UNITS_PER_SM) lk_exact_march
                 }
             }
         }
-        // ---- 4. stage A: this warp's frame rows -> E, D, T (ring slots jw % 6, (jw + 1) % 6)
+        // ---- 4. stage A: this warp's frame rows -> E, D, T (ring slots jw & 7, (jw + 1) & 7)
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const f32x2 p0 = pk(fv[rr][0], fv[rr][2]), p1 = pk(fv[rr][1], fv[rr][3]);
             const f32x2 c0 = pk(fv[rr][4], fv[rr][6]), c1 = pk(fv[rr][5], fv[rr][7]);
             const f32x2 avg0 = mul2(add2(p0, c0), half2), avg1 = mul2(add2(p1, c1), half2);  // (p + c) / 2.0
-            const int w = (int)((unsigned)(jw + rr) % XM_FRING) * XM_PITCH + wl;
+            const int w = ((jw + rr) & (XM_FRING - 1)) * XM_PITCH + wl;
             *reinterpret_cast<ulonglong2*>(sE + w) = make_ulonglong2(mul2(avg0, k125), mul2(avg1, k125));
             *reinterpret_cast<ulonglong2*>(sD + w) = make_ulonglong2(mul2(avg0, k25), mul2(avg1, k25));
             *reinterpret_cast<ulonglong2*>(sT + w) = make_ulonglong2(sub2(p0, c0), sub2(p1, c1));
