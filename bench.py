@@ -677,7 +677,7 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
     achieved = bpp * pixels_per_step / (world if rowband else 1) / (kernel_ms * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic_bytes(name, B)
     kernel = ("whole pyramidal step (all launches)" if wl["pyramidal"] else
-              {"fixed": "lk_march_kernel<true, false, true, true> (uint8 in, S8.7 out)", "exact": "lk_tile5_kernel<SRC_FRAMES>",
+              {"fixed": "lk_march_kernel<true, false, true, true> (uint8 in, S8.7 out)", "exact": "lk_exact_march_kernel<SRC_FRAMES>",
                "u8": "lk_march_kernel<true, false, true> (uint8 frames)"}.get(variant, "lk_march_kernel<true, false> (one launch per step)"))
     return {
         "name": name,

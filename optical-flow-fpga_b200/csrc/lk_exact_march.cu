@@ -9,18 +9,19 @@
 // lane-instructions per pixel, profiles/r01c) is not the arithmetic np.sum's order forces but tile overhead:
 // every 16 x 64 tile re-stages a 22 x 70 frame tile and re-derives a 20 x 68 product tile (1.5 / 1.33 pixels of
 // work per output), and every scalar float32 operation takes a full issue slot.  Here
-//   * a WARP owns two adjacent 58-column strips and marches down a band of rows, one frame row per step: every
+//   * a unit owns two adjacent 58-column strips and marches down a band of rows: every
 //     frame value is loaded, averaged and scaled once, every gradient and product formed once (the only
 //     redundancy is the 3-column halo of a strip, 6 / 64);
 //   * lane L holds columns 2L, 2L + 1 of BOTH strips, packed: one 64-bit word = the same column of strip A and
 //     strip B.  Every Sobel tap, product and window-sum addition is a Blackwell packed-pair instruction
 //     (FADD2 / FMUL2: one issue slot, two independent IEEE operations) on naturally aligned operands;
-//   * the rows in flight live in warp-private shared-memory rings (4 scaled-frame rows, 6 product rows), so a
-//     lane reads its neighbours' columns directly and the warp needs two __syncwarp() per step -- no block
-//     barrier, no shuffles;
-//   * a step handles TWO rows: with 23 KB of rings per warp only 9 warps fit an SM, so the latency has to be
-//     hidden inside the warp -- two output rows are two independent sets of accumulation chains, and they share
-//     every shared-memory load of the six product rows they read (3.75 instead of 6.25 128-bit loads per output).
+//   * the rows in flight live in shared-memory rings (8 scaled-frame rows, 8 product rows), so a lane reads its
+//     neighbours' columns directly -- no shuffles;
+//   * the rings (34.8 KB) cap an SM at six units, so the latency has to be hidden inside the unit: a unit is a CTA of
+//     TWO warps sharing one set of rings, a step handles FOUR rows (two per warp) between two barriers; a warp's two
+//     output rows are two independent sets of accumulation chains and share every shared-memory load of the six
+//     product rows they read (3.75 instead of 6.25 128-bit loads per output); frame and flow loads are issued at the
+//     top of a step and consumed at its end.
 // Per output the operations and their order are exactly lk_tile5_kernel's (scaled frame planes E = avg * 0.125,
 // D = avg * 0.25 so that a Sobel tap is one addition; zero taps contribute value * 0.0; the 25 products summed
 // like np.sum: 8 running lanes, tree, tail, + 0.0; Cramer without FMA), so the bits are the reference's.

@@ -1,4 +1,4 @@
-// lk_exact_march_kernel -- the marching exact-mode kernel for window 5 (OF_B200_EXACT=march) -- run on the CPU from its own source file
+// lk_exact_march_kernel -- the default exact-mode kernel for window 5 -- run on the CPU from its own source file
 // through its own launcher (band planning, dynamic shared memory as on the device): lk_exact_march.cu is #included
 // below and compiled by g++ on top of cuda_on_host.h (CUDA threads = OS threads, __syncwarp a barrier, packed pairs
 // two IEEE operations).  TEST INFRASTRUCTURE; tests/test_kernel_host_emulation.py builds and drives it.

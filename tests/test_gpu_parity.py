@@ -294,7 +294,7 @@ def test_exact_mode_kernel_variants_give_the_same_bits(ofb):
     """Exact mode has three switches, each read once per process, so every combination runs in a child:
     OF_B200_EXACT_REFINE = split (warp_rows_kernel<double> + tile kernel on (prev, warped)) | fused (the tile
     kernel gathers its own halo), OF_B200_TILE = v1 (lk_tile_kernel) | v2 (lk_tile5_kernel, window 5),
-    OF_B200_EXACT = march (lk_exact_march_kernel: packed pairs, warp-private shared-memory rings) | tile.
+    OF_B200_EXACT = march (lk_exact_march_kernel, the default: packed pairs, shared-memory rings) | tile.
     Single-scale on float frames (ragged shapes, one narrower than a tile) and a 3-level pyramidal run whose
     flow has both signs and leaves the frame (warp's outside -> 0 rule) must hash identically."""
     import os

@@ -50,8 +50,8 @@ def _build(tmp_path_factory, name, *more, defines=()):
 
 @pytest.fixture(scope="module", params=["lk_exact_march", "lk_tile5"])
 def emul(tmp_path_factory, request):
-    """The two exact window-5 kernels behind the same two calls: lk_tile5_kernel (the default) and lk_exact_march_kernel
-    (OF_B200_EXACT=march; through its launcher).  Every test that takes this fixture runs on both."""
+    """The two exact window-5 kernels behind the same two calls: lk_exact_march_kernel (the default; through its
+    launcher) and lk_tile5_kernel (OF_B200_EXACT=tile).  Every test that takes this fixture runs on both."""
     name = request.param
     lib = _build(tmp_path_factory, f"emul_{name}")
     frames, warped = getattr(lib, f"emul_{name}_frames"), getattr(lib, f"emul_{name}_warped")
