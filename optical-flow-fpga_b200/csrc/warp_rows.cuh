@@ -100,17 +100,21 @@ __global__ void __launch_bounds__(256) warp_rows_kernel(WarpRowsArgs a) {
     const int x0 = blockIdx.x * (256 * WR_PER_THREAD) + threadIdx.x;
     const int cur = (a.sel ? a.sel[pair] : 0) ^ a.sel_xor;
     const int H = a.H, W = a.W;
-    const size_t plane = (size_t)H * W, row = pair * plane + (size_t)y * W;
-    const float* __restrict__ fu = (cur ? a.flow_u[1] : a.flow_u[0]) + row;
-    const float* __restrict__ fv = (cur ? a.flow_v[1] : a.flow_v[0]) + row;
+    const size_t plane = (size_t)H * W;
     const float* __restrict__ img = a.curr + pair * plane;
-    float* __restrict__ out = a.warped + row;
+    // per-pair bases once, then 32-bit element offsets (H * W < 2^31) and one widening multiply-add per address:
+    // 64-bit index arithmetic per load was a twelfth of the kernel's instructions
+    const char* fub = reinterpret_cast<const char*>((cur ? a.flow_u[1] : a.flow_u[0]) + pair * plane);
+    const char* fvb = reinterpret_cast<const char*>((cur ? a.flow_v[1] : a.flow_v[0]) + pair * plane);
+    char* outb = reinterpret_cast<char*>(a.warped + pair * plane);
+    const unsigned r0 = (unsigned)y * (unsigned)W;
+    float* __restrict__ out = reinterpret_cast<float*>(outb + (size_t)r0 * 4u);
     float lu[WR_PER_THREAD], lv[WR_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < WR_PER_THREAD; ++k) {
-        const int xs = min(x0 + 256 * k, W - 1);  // keep the loads in range; the store is predicated
-        lu[k] = __ldg(fu + xs);
-        lv[k] = __ldg(fv + xs);
+        const unsigned xs = (unsigned)min(x0 + 256 * k, W - 1);  // keep the loads in range; the store is predicated
+        lu[k] = __ldg(reinterpret_cast<const float*>(fub + (size_t)(r0 + xs) * 4u));
+        lv[k] = __ldg(reinterpret_cast<const float*>(fvb + (size_t)(r0 + xs) * 4u));
     }
     if (sizeof(F) == 8) {
         // Exact flavour.  The reference's coordinate is the float64 sum y + v (lucas_kanade_pyramidal.py:88-92),
