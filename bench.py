@@ -62,6 +62,9 @@ WORKLOADS = {
     # bands over all ranks (strong scaling, all-reduce per iteration + all-gather per level in peer memory)
     "pyramidal_8k": dict(batch=4, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True),
     "pyramidal_8k_exact": dict(batch=1, H=4320, W=7680, pyramidal=True, levels=5, iters=10, rowband=True, variant="exact"),
+    # verification_config.yaml:99-103, preset large_window (3 levels, 7x7 window, 3 iterations) and its single-scale kernel
+    "single_1080p_w7": dict(batch=256, H=1080, W=1920, pyramidal=False, levels=1, iters=1, window=7),
+    "pyramidal_4k_w7": dict(batch=16, H=2160, W=3840, pyramidal=True, levels=3, iters=3, window=7),
 }
 # measured next to the primary workload by a default run (the `workloads` map of the JSON line)
 DEFAULT_EXTRA = ["single_4k", "single_1080p_u8", "single_1080p_exact", "fixed_1080p", "pyramidal_4k", "pyramidal_4k_exact",
@@ -185,16 +188,16 @@ class ClockSampler:
 # CPU oracle timing (cpu_baseline leg and the --impl reference arm)
 # ---------------------------------------------------------------------------------------
 def _oracle_job(args):
-    kind, seed, rows, H, W, levels, iters = args
+    kind, seed, rows, H, W, levels, iters, window = args
     import synthetic
     from oracle import lk_float_oracle as orc
 
     prev, curr, _ = synthetic.make_pairs_numpy(1, rows, W, seed=seed)
     t0 = time.perf_counter()
     if kind == "pyramidal":
-        orc.lucas_kanade_pyramidal(prev[0], curr[0], levels, WINDOW, iters)
+        orc.lucas_kanade_pyramidal(prev[0], curr[0], levels, window, iters)
     else:
-        orc.lucas_kanade_single_scale(prev[0], curr[0], WINDOW)
+        orc.lucas_kanade_single_scale(prev[0], curr[0], window)
     return time.perf_counter() - t0, rows * W
 
 
@@ -223,7 +226,7 @@ def run_oracle_sample(pool, cores: int, wl: dict, rows: int, jobs: int, seed0: i
     running at the same time.  Frame synthesis is not timed: the step's time is the slowest
     worker's oracle time.  Returns (Mpixel/s, pixels, seconds)."""
     kind = "pyramidal" if wl["pyramidal"] else "single"
-    work = [(kind, seed0 + j, rows, wl["H"], wl["W"], wl["levels"], wl["iters"]) for j in range(jobs)]
+    work = [(kind, seed0 + j, rows, wl["H"], wl["W"], wl["levels"], wl["iters"], wl.get("window", WINDOW)) for j in range(jobs)]
     res = pool.map(_oracle_job, work, chunksize=1)
     pixels = sum(r[1] for r in res)
     secs = max(r[0] for r in res)
@@ -310,18 +313,19 @@ def reference_arm(args, wl, rank: int, world: int):
 
 
 def workload_config(name: str, wl: dict) -> dict:
+    win = wl.get("window", WINDOW)
     if wl["pyramidal"]:
         desc = (f"{wl['levels']}-level pyramidal LK, {wl['iters']} iterations/level, batch of {wl['batch']} synthetic "
-                f"{wl['W']}x{wl['H']} float32 frame pairs per GPU, 5x5 window")
+                f"{wl['W']}x{wl['H']} float32 frame pairs per GPU, {win}x{win} window")
     else:
-        desc = f"single-scale LK, batch of {wl['batch']} synthetic {wl['W']}x{wl['H']} float32 frame pairs per GPU, 5x5 window"
+        desc = f"single-scale LK, batch of {wl['batch']} synthetic {wl['W']}x{wl['H']} float32 frame pairs per GPU, {win}x{win} window"
     return {
         "workload": desc,
         "name": name,
         "batch_per_gpu": wl["batch"],
         "height": wl["H"],
         "width": wl["W"],
-        "window": WINDOW,
+        "window": wl.get("window", WINDOW),
         "mode": {"exact": "exact (reference operation order)", "fixed": "fixed-point S8.7 (RTL datapath)",
                  "u8": "fast, uint8 frames in"}.get(wl.get("variant"), "fast"),
         "l2": "per-step inputs + outputs are far larger than the 126 MB L2, so no flush between iterations",
@@ -469,7 +473,7 @@ def measure_e2e(env: Env, name: str, wl: dict, prev, curr, u, steps: int):
         api = "of_lk_pyramidal_f32 (host buffers, pinned), passes of a few pairs pipelined H2D/kernels/D2H on 3 streams"
 
         def call():
-            of_b200.lk_pyramidal_batch(hp, hc, wl["levels"], WINDOW, wl["iters"], mode, out=(hu, hv))
+            of_b200.lk_pyramidal_batch(hp, hc, wl["levels"], wl.get("window", WINDOW), wl["iters"], mode, out=(hu, hv))
     elif fixed:
         api = "of_lk_single_scale_fx (host buffers, pinned: uint8 frames in, int16 S8.7 flow out), chunked H2D/kernel/D2H on 3 streams"
 
@@ -479,13 +483,13 @@ def measure_e2e(env: Env, name: str, wl: dict, prev, curr, u, steps: int):
         api = "of_lk_single_scale_u8 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams"
 
         def call():
-            of_b200.lk_single_scale_u8_batch(hp, hc, WINDOW, of_b200.MODE_FAST, out=(hu, hv))
+            of_b200.lk_single_scale_u8_batch(hp, hc, wl.get("window", WINDOW), of_b200.MODE_FAST, out=(hu, hv))
     else:
         mode = of_b200.MODE_EXACT if variant == "exact" else of_b200.MODE_FAST
         api = "of_lk_single_scale_f32 (host buffers, pinned), chunked H2D/kernel/D2H on 3 streams"
 
         def call():
-            of_b200.lk_single_scale_batch(hp, hc, WINDOW, mode, out=(hu, hv))
+            of_b200.lk_single_scale_batch(hp, hc, wl.get("window", WINDOW), mode, out=(hu, hv))
     e2e_steps = max(1, min(steps, 5))
     for _ in range(2):  # warm-up: arena allocation, streams
         call()
@@ -555,11 +559,11 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
         p8, c8 = prev.to(torch.uint8), curr.to(torch.uint8)
 
         def step():
-            of_b200.lk_single_scale_u8_dev(p8.data_ptr(), c8.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, WINDOW, stream)
+            of_b200.lk_single_scale_u8_dev(p8.data_ptr(), c8.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, wl.get("window", WINDOW), stream)
     elif variant == "exact" and not wl["pyramidal"]:
         def step():
             of_b200.lk_single_scale_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
-                                        WINDOW, of_b200.MODE_EXACT, stream)
+                                        wl.get("window", WINDOW), of_b200.MODE_EXACT, stream)
     elif rowband:
         import distributed as ofd
 
@@ -570,7 +574,7 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
 
             def step():
                 for b in range(B):
-                    ub, vb = ofd.lk_pyramidal_rowbands(prev[b], curr[b], wl["levels"], WINDOW, wl["iters"],
+                    ub, vb = ofd.lk_pyramidal_rowbands(prev[b], curr[b], wl["levels"], wl.get("window", WINDOW), wl["iters"],
                                                        mode=pyr_mode, comm=comm, backend=backend, to_host=False)
                     u[b].copy_(ub)
                     v[b].copy_(vb)
@@ -582,7 +586,7 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
             # in flight at once, each on its own stream with its own arena, so the launch-latency-bound
             # kernels of the coarse levels and the peer gathers of one pair overlap with the other pairs' work.
             n_lanes = max(1, min(B, int(os.environ.get("OF_B200_ROWBAND_LANES", "4"))))
-            lanes = ofd.PeerRowbandLanes(H, W, wl["levels"], WINDOW, wl["iters"], pyr_mode, lanes=n_lanes)
+            lanes = ofd.PeerRowbandLanes(H, W, wl["levels"], wl.get("window", WINDOW), wl["iters"], pyr_mode, lanes=n_lanes)
 
             def enqueue():
                 lanes.run_batch(prev, curr, u, v)
@@ -603,12 +607,12 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
 
         def step():
             of_b200.lk_pyramidal_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
-                                     wl["levels"], WINDOW, wl["iters"], pyr_mode, ws.data_ptr(), ws_bytes,
+                                     wl["levels"], wl.get("window", WINDOW), wl["iters"], pyr_mode, ws.data_ptr(), ws_bytes,
                                      None, None, stream)
     else:
         def step():
             of_b200.lk_single_scale_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W,
-                                        WINDOW, of_b200.MODE_FAST, stream)
+                                        wl.get("window", WINDOW), of_b200.MODE_FAST, stream)
 
     for _ in range(max(warmup, 3)):
         step()
@@ -643,7 +647,7 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
             executed = np.mean(np.stack([np.asarray(t[0], dtype=np.float64) for t in tr]), axis=0)
         elif not rowband:
             it_dev = torch.zeros((B, L), dtype=torch.int32, device=dev)
-            of_b200.lk_pyramidal_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, L, WINDOW, I,
+            of_b200.lk_pyramidal_dev(prev.data_ptr(), curr.data_ptr(), u.data_ptr(), v.data_ptr(), B, H, W, L, wl.get("window", WINDOW), I,
                                      pyr_mode, ws.data_ptr(), ws_bytes, it_dev.data_ptr(), None, stream)
             torch.cuda.synchronize()
             executed = it_dev.to(torch.float64).mean(dim=0).cpu().numpy()
@@ -745,15 +749,15 @@ def check_parity(env: Env, name, wl, prev, curr, u, v, fixed_out, rowband):
     ok = True
     worst, frac_big, mean_diff, n_big = 0.0, 0.0, 0.0, 0
     for b in idx:
-        key = (H, W, wl["levels"], wl["iters"], wl["pyramidal"], b, bool(rowband))
+        key = (H, W, wl["levels"], wl["iters"], wl["pyramidal"], b, bool(rowband), wl.get("window", WINDOW))
         if key not in _ORACLE_CACHE:
             p_h, c_h = prev[b].cpu().numpy(), curr[b].cpu().numpy()
             if big:
-                _ORACLE_CACHE[key] = of_b200.lk_pyramidal(p_h, c_h, wl["levels"], WINDOW, wl["iters"], mode=of_b200.MODE_EXACT)
+                _ORACLE_CACHE[key] = of_b200.lk_pyramidal(p_h, c_h, wl["levels"], wl.get("window", WINDOW), wl["iters"], mode=of_b200.MODE_EXACT)
             elif wl["pyramidal"]:
-                _ORACLE_CACHE[key] = orc.lucas_kanade_pyramidal(p_h, c_h, wl["levels"], WINDOW, wl["iters"])
+                _ORACLE_CACHE[key] = orc.lucas_kanade_pyramidal(p_h, c_h, wl["levels"], wl.get("window", WINDOW), wl["iters"])
             else:
-                _ORACLE_CACHE[key] = orc.lucas_kanade_single_scale(p_h, c_h, WINDOW)
+                _ORACLE_CACHE[key] = orc.lucas_kanade_single_scale(p_h, c_h, wl.get("window", WINDOW))
         uo, vo = _ORACLE_CACHE[key]
         ug, vg = u[b].cpu().numpy(), v[b].cpu().numpy()
         ok &= bool(np.array_equal(ug.view(np.uint32), uo.view(np.uint32)))
@@ -773,7 +777,7 @@ def check_parity(env: Env, name, wl, prev, curr, u, v, fixed_out, rowband):
         ws1 = torch.empty(of_b200.lk_pyramidal_workspace_bytes(1, H, W, wl["levels"], wl["iters"]), dtype=torch.uint8, device=env.dev)
         u1, v1 = torch.empty_like(prev[0]), torch.empty_like(prev[0])
         of_b200.lk_pyramidal_dev(prev[B - 1].data_ptr(), curr[B - 1].data_ptr(), u1.data_ptr(), v1.data_ptr(), 1, H, W,
-                                 wl["levels"], WINDOW, wl["iters"], pyr_mode, ws1.data_ptr(), ws1.numel(), None,
+                                 wl["levels"], wl.get("window", WINDOW), wl["iters"], pyr_mode, ws1.data_ptr(), ws1.numel(), None,
                                  None, stream)
         torch.cuda.synchronize()
         parity["rowband_bit_equal_to_single_gpu"] = bool(torch.equal(u1.view(torch.int32), u[B - 1].view(torch.int32)) and

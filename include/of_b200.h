@@ -190,7 +190,7 @@ int of_lk_single_scale_fx_dev(const uint8_t* prev, const uint8_t* curr, int16_t*
  * for bit, with 10 instead of 16 bytes of HBM traffic per pixel in fast mode. */
 int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int height,
                           int width, int window, int mode);
-/* device buffers; fast mode only; needs window 5, width % 16 == 0, 16-byte aligned planes */
+/* device buffers; fast mode only; needs window 5 or 7, width % 16 == 0, 16-byte aligned planes */
 int of_lk_single_scale_u8_dev(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int height,
                               int width, int window, void* stream);
 /* read one [height][width] uint8 frame from a .bin (raw) or .mem (hex lines) file into host memory */

@@ -190,7 +190,7 @@ int single_scale_dev(const float* prev, const float* curr, float* u, float* v, i
     const bool aligned = ((reinterpret_cast<uintptr_t>(prev) | reinterpret_cast<uintptr_t>(curr) |
                            reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
     if (mode == OF_MODE_FAST && aligned && lk_march_supported(H, W, window)) {
-        OF_CUDA(launch_lk_march(prev, curr, u, v, batch, H, W, 0, &cnt.n, stream));
+        OF_CUDA(launch_lk_march(prev, curr, u, v, batch, H, W, window, 0, &cnt.n, stream));
         return OF_OK;
     }
     TileArgs a;
@@ -357,7 +357,7 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                                          p.h[k + 1], p.w[k + 1], p.h[k], p.w[k], 0, p.h[k], &cnt.n, stream));
         }
         // fast mode: the register-marching kernel where the level allows TMA (width % 4 == 0,
-        // window 5); otherwise, and always in exact mode, the reference-order tile kernel
+        // window 5 or 7); otherwise, and always in exact mode, the reference-order kernels
         RefineArgs ra;
         memset(&ra, 0, sizeof(ra));
         ra.prev = lp[k];
@@ -372,6 +372,7 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         ra.partial = partial;
         ra.H = p.h[k];
         ra.W = p.w[k];
+        ra.window = window;
         ra.row_lo = 0;
         ra.row_hi = p.h[k];
         ra.own_lo = 0;
@@ -891,6 +892,7 @@ static int refine_dev_impl(const float* prev, const float* curr, float* flow_in_
     ra.partial = partial;
     ra.H = height;
     ra.W = width;
+    ra.window = window;
     ra.row_lo = row_lo;
     ra.row_hi = row_hi;
     ra.own_lo = own_lo;
@@ -1015,10 +1017,10 @@ int of_lk_single_scale_u8_dev(const uint8_t* prev, const uint8_t* curr, float* u
     OF_TRY(need_device());
     if (!lk_march_u8_supported(prev, curr, u, v, height, width, window))
         return fail(OF_ERR_UNSUPPORTED,
-                    "the device-buffer uint8 entry point needs window 5, width % 16 == 0 and 16-byte aligned planes "
+                    "the device-buffer uint8 entry point needs window 5 or 7, width % 16 == 0 and 16-byte aligned planes "
                     "(of_lk_single_scale_u8 takes any frame)");
     Counter cnt;
-    OF_CUDA(launch_lk_march_u8(prev, curr, u, v, batch, height, width, &cnt.n, static_cast<cudaStream_t>(stream)));
+    OF_CUDA(launch_lk_march_u8(prev, curr, u, v, batch, height, width, window, &cnt.n, static_cast<cudaStream_t>(stream)));
     return OF_OK;
 }
 
@@ -1055,7 +1057,7 @@ int of_lk_single_scale_u8(const uint8_t* prev, const uint8_t* curr, float* u, fl
         OF_CUDA(cudaMemcpyAsync(d8[s][0], prev + b0 * plane, (size_t)nb * plane, cudaMemcpyHostToDevice, st));
         OF_CUDA(cudaMemcpyAsync(d8[s][1], curr + b0 * plane, (size_t)nb * plane, cudaMemcpyHostToDevice, st));
         if (mode == OF_MODE_FAST && lk_march_u8_supported(d8[s][0], d8[s][1], df[s][2], df[s][3], height, width, window)) {
-            OF_CUDA(launch_lk_march_u8(d8[s][0], d8[s][1], df[s][2], df[s][3], nb, height, width, &cnt.n, st));
+            OF_CUDA(launch_lk_march_u8(d8[s][0], d8[s][1], df[s][2], df[s][3], nb, height, width, window, &cnt.n, st));
         } else {
             for (int j = 0; j < 2; ++j) {
                 OF_TRY(hp->arena.get(s * 4 + j, per_chunk * plane * sizeof(float), reinterpret_cast<void**>(&df[s][j])));

@@ -97,13 +97,13 @@ struct MarchArgs {
 };
 bool lk_march_supported(int H, int W, int window);
 // force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
-cudaError_t launch_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W,
+cudaError_t launch_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int window,
                             int force_path, int* launches, cudaStream_t stream);
 
 // uint8 ingest of the same kernel (10 B per pixel): needs W % 16 == 0 and 16-byte aligned planes
 bool lk_march_u8_supported(const uint8_t* prev, const uint8_t* curr, const float* u, const float* v, int H, int W, int window);
 cudaError_t launch_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int H, int W,
-                               int* launches, cudaStream_t stream);
+                               int window, int* launches, cudaStream_t stream);
 // the RTL's fixed-point datapath on the same marching kernel (6 B per pixel); same frame requirements
 bool lk_march_fx_supported(const uint8_t* prev, const uint8_t* curr, const int16_t* u, const int16_t* v, int H, int W);
 cudaError_t launch_lk_march_fx(const uint8_t* prev, const uint8_t* curr, int16_t* u, int16_t* v, int batch, int H, int W,
@@ -121,6 +121,7 @@ struct RefineArgs {
     const int* done;
     double* partial;    // [pair][units_per_pair][2]
     int H, W;
+    int window;         // 5 or 7 (lk_refine_supported)
     // Row-band mode: only rows [row_lo, row_hi) are computed (the frame and the flow buffers are
     // still full-size), and only rows [own_lo, own_hi) enter the |du|, |dv| sums.  Whole frame:
     // 0, H, 0, H.  row_lo must be even so that rows pair up the same way on every rank.

@@ -330,6 +330,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         ra.partial = partial;
         ra.H = h;
         ra.W = w;
+        ra.window = c.window;
         ra.own_lo = a;
         ra.own_hi = b;
         const bool fast_level = (c.mode == OF_MODE_FAST) && lk_refine_supported(ra, c.window);

@@ -106,11 +106,13 @@ static_assert(HOST_LOADW == LOADW && HOST_U8_BOX_W == U8_BOX_W, "box widths of t
 
 extern "C" {
 // force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
-int emul_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int force_path) {
-    return (int)launch_lk_march(prev, curr, u, v, batch, H, W, force_path, nullptr, nullptr);
+int emul_lk_march(const float* prev, const float* curr, float* u, float* v, int batch, int H, int W, int force_path,
+                  int window) {
+    if (!lk_march_supported(H, W, window)) return -1;
+    return (int)launch_lk_march(prev, curr, u, v, batch, H, W, window, force_path, nullptr, nullptr);
 }
-int emul_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int H, int W) {
-    return (int)launch_lk_march_u8(prev, curr, u, v, batch, H, W, nullptr, nullptr);
+int emul_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* v, int batch, int H, int W, int window) {
+    return (int)launch_lk_march_u8(prev, curr, u, v, batch, H, W, window, nullptr, nullptr);
 }
 // One fast-mode refinement iteration.  form 0: split (warp_rows_kernel<float> + lk_march_kernel<REFINE>), the
 // per-unit sums go to `partial`; form 1: split with the iteration's tail fused into the marching kernel (ticket
@@ -118,7 +120,7 @@ int emul_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* 
 int emul_lk_refine(int form, const float* prev, const float* curr, float* flow_u0, float* flow_v0, float* flow_u1,
                    float* flow_v1, int* sel, int sel_xor, int* done, double* partial, float* warped, unsigned* counter,
                    int* iters_executed, float* residuals, int max_iters, int iteration, int batch, int H, int W, int row_lo,
-                   int row_hi, int own_lo, int own_hi) {
+                   int row_hi, int own_lo, int own_hi, int window) {
     RefineArgs ra;
     std::memset(&ra, 0, sizeof(ra));
     ra.prev = prev;
@@ -133,11 +135,12 @@ int emul_lk_refine(int form, const float* prev, const float* curr, float* flow_u
     ra.partial = partial;
     ra.H = H;
     ra.W = W;
+    ra.window = window;
     ra.row_lo = row_lo;
     ra.row_hi = row_hi;
     ra.own_lo = own_lo;
     ra.own_hi = own_hi;
-    if (!lk_refine_supported(ra, 5)) return -1;
+    if (!lk_refine_supported(ra, window)) return -1;
     if (form == 1) {
         ra.tail.counter = counter;
         ra.tail.peers = 0;

@@ -504,10 +504,10 @@ def test_metrics_kernels_source_on_cpu(tmp_path_factory):
 @pytest.fixture(scope="module")
 def emul_march(tmp_path_factory):
     lib = _build(tmp_path_factory, "emul_lk_march")
-    lib.emul_lk_march.argtypes = [_vp] * 4 + [_i] * 4
-    lib.emul_lk_march_u8.argtypes = [_vp] * 4 + [_i] * 3
+    lib.emul_lk_march.argtypes = [_vp] * 4 + [_i] * 5
+    lib.emul_lk_march_u8.argtypes = [_vp] * 4 + [_i] * 4
     lib.emul_lk_march_fx.argtypes = [_vp] * 4 + [_i] * 4
-    lib.emul_lk_refine.argtypes = [_i] + [_vp] * 6 + [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 9
+    lib.emul_lk_refine.argtypes = [_i] + [_vp] * 6 + [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 10
     lib.emul_lk_refine_units_per_pair.argtypes = [_i, _i, _i]
     return lib
 
@@ -515,36 +515,44 @@ def emul_march(tmp_path_factory):
 TMA_OR_ERROR, PLAIN_LOADS = 1, 2
 
 
+@pytest.mark.parametrize("window", [5, 7])
 @pytest.mark.parametrize("shape", [(5, 8), (9, 120), (24, 128), (17, 132), (40, 248), (31, 364)])
-def test_marching_kernel_source_on_cpu_uint8_valued_frames(emul_march, shape):
+def test_marching_kernel_source_on_cpu_uint8_valued_frames(emul_march, shape, window):
     """Fast mode is bit-identical to the reference on uint8-valued frames (every partial sum is exact, so the
     separable association does not matter): both load paths -- the TMA ring (tensor-map boxes with zero fill, row-by-row
     edge chunks, patched border columns) and plain global loads -- on widths that end inside a strip, one warp wide,
-    several strips wide, heights that are not a multiple of the 8-row chunk."""
+    several strips wide, heights that are not a multiple of the 8-row chunk.  Window 5 and 7 (the large_window preset,
+    verification_config.yaml:99-103) are the same kernel with a 5- or 7-row state."""
     h, w = shape
     rng = np.random.default_rng(h * w)
-    p = rng.integers(0, 256, (2, h, w)).astype(f32)
-    c = rng.integers(0, 256, (2, h, w)).astype(f32)
-    want = [orc.lucas_kanade_single_scale(p[b], c[b], 5) for b in range(2)]
+    # exactness needs every window sum below 2^16 (multiples of 1/256 in a 24-bit significand): full-range white noise
+    # stays below with 25 taps, with 49 taps a few pixels per frame cross it (and then differ in the last bit), so the
+    # window-7 frames use half the range -- any natural frame has far less gradient energy than either
+    top = 256 if window == 5 else 128
+    p = rng.integers(0, top, (2, h, w)).astype(f32)
+    c = rng.integers(0, top, (2, h, w)).astype(f32)
+    want = [orc.lucas_kanade_single_scale(p[b], c[b], window) for b in range(2)]
     for path in (TMA_OR_ERROR, PLAIN_LOADS):
         u, v = np.full_like(p, np.nan), np.full_like(p, np.nan)
-        assert emul_march.emul_lk_march(ptr(p), ptr(c), ptr(u), ptr(v), 2, h, w, path) == 0
+        assert emul_march.emul_lk_march(ptr(p), ptr(c), ptr(u), ptr(v), 2, h, w, path, window) == 0
         for b in range(2):
             assert np.array_equal(bits(u[b]), bits(want[b][0])) and np.array_equal(bits(v[b]), bits(want[b][1])), (path, b)
 
 
+@pytest.mark.parametrize("window", [5, 7])
 @pytest.mark.parametrize("shape", [(24, 128), (33, 256), (20, 144)])
-def test_marching_kernel_uint8_ingest_and_fixed_point_flavours(emul_march, shape):
+def test_marching_kernel_uint8_ingest_and_fixed_point_flavours(emul_march, shape, window):
     h, w = shape
     rng = np.random.default_rng(h + w)
-    p8 = rng.integers(0, 256, (2, h, w)).astype(np.uint8)
-    c8 = rng.integers(0, 256, (2, h, w)).astype(np.uint8)
+    top = 256 if window == 5 else 128  # see test_marching_kernel_source_on_cpu_uint8_valued_frames
+    p8 = rng.integers(0, top, (2, h, w)).astype(np.uint8)
+    c8 = rng.integers(0, top, (2, h, w)).astype(np.uint8)
     u, v = np.full((2, h, w), np.nan, f32), np.full((2, h, w), np.nan, f32)
-    assert emul_march.emul_lk_march_u8(ptr(p8), ptr(c8), ptr(u), ptr(v), 2, h, w) == 0
+    assert emul_march.emul_lk_march_u8(ptr(p8), ptr(c8), ptr(u), ptr(v), 2, h, w, window) == 0
     for b in range(2):
-        uo, vo = orc.lucas_kanade_single_scale(p8[b].astype(f32), c8[b].astype(f32), 5)
+        uo, vo = orc.lucas_kanade_single_scale(p8[b].astype(f32), c8[b].astype(f32), window)
         assert np.array_equal(bits(u[b]), bits(uo)) and np.array_equal(bits(v[b]), bits(vo))
-    for quirk in (1, 0):
+    for quirk in ((1, 0) if window == 5 else ()):  # the RTL's window is 5 x 5
         u16, v16 = np.full((2, h, w), 77, np.int16), np.full((2, h, w), 77, np.int16)
         assert emul_march.emul_lk_march_fx(ptr(p8), ptr(c8), ptr(u16), ptr(v16), 2, h, w, quirk) == 0
         for b in range(2):
@@ -552,7 +560,7 @@ def test_marching_kernel_uint8_ingest_and_fixed_point_flavours(emul_march, shape
             assert np.array_equal(u16[b], uo) and np.array_equal(v16[b], vo), (quirk, b)
 
 
-def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state=None, rows=None):
+def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state=None, rows=None, window=5):
     b, h, w = prev.shape
     out_u, out_v = np.full_like(fu, 9.0), np.full_like(fv, 9.0)
     sel = np.zeros(b, np.int32) if state is None else state["sel"]
@@ -565,12 +573,13 @@ def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state
     warped = np.zeros_like(prev)
     cnt = np.zeros(b, np.uint32)
     rc = lib.emul_lk_refine(form, ptr(prev), ptr(curr), ptr(fu), ptr(fv), ptr(out_u), ptr(out_v), ptr(sel), 0, ptr(done),
-                            ptr(partial), ptr(warped), ptr(cnt), ptr(executed), ptr(resid), 4, iteration, b, h, w, lo, hi, lo, hi)
+                            ptr(partial), ptr(warped), ptr(cnt), ptr(executed), ptr(resid), 4, iteration, b, h, w, lo, hi, lo, hi, window)
     assert rc == 0
     return out_u, out_v, partial, dict(sel=sel, done=done, executed=executed, resid=resid)
 
 
-def test_fast_refinement_iteration_source_on_cpu(emul_march):
+@pytest.mark.parametrize("window", [5, 7])
+def test_fast_refinement_iteration_source_on_cpu(emul_march, window):
     """One fast-mode iteration in its three forms.  Split and fused give the same bits; against the reference the
     iteration is tolerance-level (float32 warp fraction, separable window sums), so the comparison is statistical:
     flow_out - flow_in equals the oracle's increment except where the 2 x 2 system is ill-conditioned."""
@@ -582,18 +591,18 @@ def test_fast_refinement_iteration_source_on_cpu(emul_march):
     curr = np.stack([shift(prev[0], (0.4, -0.7), order=1, mode="nearest"), shift(prev[1], (-0.6, 0.3), order=1, mode="nearest")]).astype(f32)
     fu = (rng.standard_normal((b, h, w)) * 0.2).astype(f32)
     fv = (rng.standard_normal((b, h, w)) * 0.2).astype(f32)
-    split_u, split_v, split_part, _ = _refine_once(emul_march, 0, prev, curr, fu, fv)
-    fused_u, fused_v, fused_part, _ = _refine_once(emul_march, 2, prev, curr, fu, fv)
+    split_u, split_v, split_part, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, window=window)
+    fused_u, fused_v, fused_part, _ = _refine_once(emul_march, 2, prev, curr, fu, fv, window=window)
     assert np.array_equal(bits(split_u), bits(fused_u)) and np.array_equal(bits(split_v), bits(fused_v))
     # the sums of |du|, |dv| are formed differently (four float32 magnitudes are added before widening in one form)
     assert split_part.sum(axis=1) == pytest.approx(fused_part.sum(axis=1), rel=1e-8)
     for k in range(b):
-        du, dv = orc.lucas_kanade_single_scale(prev[k], orc.warp_image(curr[k], fu[k], fv[k]), 5)
+        du, dv = orc.lucas_kanade_single_scale(prev[k], orc.warp_image(curr[k], fu[k], fv[k]), window)
         err = np.maximum(np.abs(split_u[k] - (fu[k] + du)), np.abs(split_v[k] - (fv[k] + dv)))
         assert np.median(err) < 1e-5 and (err > 1e-3).mean() < 0.02
         assert split_part[k, :, 0].sum() == pytest.approx(np.abs(du).astype(np.float64).sum(), rel=1e-3)
     # rows [row_lo, row_hi) only (row-band mode): the same bits on those rows, nothing written outside
-    band_u, band_v, _, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, rows=(8, 30))
+    band_u, band_v, _, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, rows=(8, 30), window=window)
     assert np.array_equal(bits(band_u[:, 8:30]), bits(split_u[:, 8:30])) and np.array_equal(bits(band_v[:, 8:30]), bits(split_v[:, 8:30]))
     assert (band_u[:, :8] == 9.0).all() and (band_u[:, 30:] == 9.0).all()
 
