@@ -222,7 +222,7 @@ struct PyrPlan {
     std::vector<int> h, w;                      // k = 0 finest ... L-1 coarsest
     std::vector<size_t> prev_off, curr_off;      // k >= 1
     std::vector<size_t> au_off, av_off, bu_off, bv_off;  // flow ping-pong (A of k = 0 is the caller's u, v)
-    std::vector<size_t> warped_off;                      // warped current frame (split refinement)
+    std::vector<size_t> warped_off, warped2_off;         // warped current frame (split refinement), ping-pong
     size_t partial_off = 0, sel_off = 0, done_off = 0, cnt_off = 0, total = 0;
     int max_blocks = 0;
 };
@@ -249,6 +249,7 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
     p.bu_off.assign(levels, 0);
     p.bv_off.assign(levels, 0);
     p.warped_off.assign(levels, 0);
+    p.warped2_off.assign(levels, 0);
     p.max_blocks = 0;
     for (int k = 0; k < levels; ++k) {
         const size_t bytes = align_up((size_t)batch * p.h[k] * p.w[k] * sizeof(float));
@@ -261,6 +262,7 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
         p.bu_off[k] = off; off += bytes;
         p.bv_off[k] = off; off += bytes;
         p.warped_off[k] = off; off += bytes;
+        p.warped2_off[k] = off; off += bytes;
         const int nb = lk_tile_blocks_per_pair(p.h[k], p.w[k]);
         if (nb > p.max_blocks) p.max_blocks = nb;
     }
@@ -286,6 +288,17 @@ bool refine_split() {
 #ifndef OF_EXACT_REFINE_SPLIT_DEFAULT
 #define OF_EXACT_REFINE_SPLIT_DEFAULT 1  // split passed the GPU suite (profiles/r01c_pytest_gpu_exact_v2.log)
 #endif
+// split refinement: the marching kernel warps the next iteration's input itself (default); OF_B200_REFINE_WARP=rows
+// keeps one warp_rows launch per iteration (A/B measurements)
+bool refine_chain_warp() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OF_B200_REFINE_WARP");
+        v = (e && std::string(e) == "rows") ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // exact-mode refinement: "split" = warp kernel with float64 fractions + the tile kernel on (prev, warped)
 // ; "fused" = the tile kernel gathers its halo tile itself (the first implementation: 1.5 gathers per
 // pixel at 16 warps per SM, latency-bound).  Same bits; OF_B200_EXACT_REFINE=split|fused picks.
@@ -380,8 +393,14 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         const bool fast_level = (mode == OF_MODE_FAST) && lk_refine_supported(ra, window);
         // split refinement: the marching kernel's last warp per pair also does the convergence step
         const bool fused_tail = fast_level && refine_split();
+        // ... and its epilogue warps the current frame through the flow it has just produced, so only the level's
+        // first iteration launches warp_rows; the two warped planes alternate (bands run independently)
+        const bool chain_warp = fused_tail && refine_chain_warp();
         for (int it = 0; it < iterations; ++it) {
             if (fast_level) {
+                float* warped_it = F((chain_warp && (it & 1)) ? p.warped2_off[k] : p.warped_off[k]);
+                ra.warped_ready = chain_warp && it > 0;
+                ra.warped_next = (chain_warp && it + 1 < iterations) ? F((it & 1) ? p.warped_off[k] : p.warped2_off[k]) : nullptr;
                 if (fused_tail) {
                     ra.tail.counter = reinterpret_cast<unsigned*>(ws + p.cnt_off);
                     ra.tail.peers = 0;
@@ -393,11 +412,11 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                     ra.tail.residuals = resid_dev ? resid_dev + (size_t)ref_level * iterations * 2 : nullptr;
                     ra.tail.resid_pair_stride = (size_t)levels * iterations * 2;
                     ra.tail.iteration = it;
-                    OF_CUDA(launch_lk_refine_split(ra, F(p.warped_off[k]), batch, &cnt.n, stream));
+                    OF_CUDA(launch_lk_refine_split(ra, warped_it, batch, &cnt.n, stream));
                     continue;
                 }
                 if (refine_split())
-                    OF_CUDA(launch_lk_refine_split(ra, F(p.warped_off[k]), batch, &cnt.n, stream));
+                    OF_CUDA(launch_lk_refine_split(ra, warped_it, batch, &cnt.n, stream));
                 else
                     OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, stream));
             } else {

@@ -94,6 +94,10 @@ struct MarchArgs {
     int16_t* v16;
     int fx_quirk;
     IterTail tail;  // REFINE: tail.counter != nullptr fuses the iteration's convergence step into the kernel
+    // REFINE, optional: the kernel also warps the NEXT iteration's input -- warped_next[y][x] = bilinear(warp_src,
+    // y + flow_out_v, x + flow_out_u) for every pixel it writes (the flow is in registers, warp_rows' arithmetic)
+    const float* warp_src;  // the level's current frame, unwarped
+    float* warped_next;     // nullable
 };
 bool lk_march_supported(int H, int W, int window);
 // force_path: 0 = TMA when the pointers allow it, 1 = TMA or error, 2 = plain global loads
@@ -129,6 +133,11 @@ struct RefineArgs {
     int n_strips, n_bands, band_rows;  // filled by the launcher
     long long n_units;
     IterTail tail;  // split form only: counter != nullptr -> the marching kernel finishes the iteration itself
+    // split form only.  warped_ready: `warped` already holds warp(curr, flow_in) on the rows this launch reads (the
+    // previous iteration's launch wrote it through its warped_next) -- no warp_rows launch.  warped_next (nullable):
+    // where this launch leaves warp(curr, flow_out) of the rows it computes, for the next iteration.
+    int warped_ready;
+    float* warped_next;
 };
 bool lk_refine_supported(const RefineArgs& a, int window);
 int lk_refine_units_per_pair(int batch, int rows, int W);

@@ -64,9 +64,18 @@ __device__ __forceinline__ F warp_fraction(float v, float floor_v) {
     return (F)v - (F)floor_v;
 }
 
+// Where one sample's four taps lie (32-bit element offsets from the frame's base), its fractions and whether it
+// lies inside the frame: the address half of a sample, shared by every kernel that warps (the loads differ:
+// registers here, cp.async into shared memory in the marching kernel's epilogue).
 template <typename F>
-__device__ __forceinline__ void warp_gather_magic(const float* __restrict__ img, int H, int W, int yc, int xc, float v,
-                                                  float u, WarpTapT<F>& t) {
+struct WarpAddrT {
+    unsigned o00, o01, o10, o11;
+    F fy, fx;
+    bool inside;
+};
+
+template <typename F>
+__device__ __forceinline__ void warp_address_magic(int H, int W, int yc, int xc, float v, float u, WarpAddrT<F>& t) {
     const float magic = 12582912.0f;  // 0x4B400000
     const float tv = __fadd_rd(v, magic), tu = __fadd_rd(u, magic);
     t.fy = warp_fraction<F>(v, tv - magic);
@@ -81,15 +90,76 @@ __device__ __forceinline__ void warp_gather_magic(const float* __restrict__ img,
     const int ys = min(max(y0, 0), H - 1), xs = min(max(x0, 0), W - 1);
     // The tap past the last row / column has weight exactly 0 (SciPy mirrors its index there);
     // any finite in-frame value gives the same sum, so it simply re-reads the last one.
-    const unsigned o00 = (unsigned)(ys * W + xs);
-    const unsigned o01 = o00 + ((xs < W - 1) ? 1u : 0u);
+    t.o00 = (unsigned)(ys * W + xs);
+    t.o01 = t.o00 + ((xs < W - 1) ? 1u : 0u);
     const unsigned dy = (ys < H - 1) ? (unsigned)W : 0u;
-    // one widening multiply-add per address (IMAD.WIDE.U32) instead of a 64-bit add + shift pair
+    t.o10 = t.o00 + dy;
+    t.o11 = t.o01 + dy;
+}
+
+// N samples of one lane on row y (columns xc[k], flow (lu[k], lv[k])).  Integer / fraction split of every sample
+// first; if the 2x2 taps of ALL samples of the warp lie strictly inside the frame (the common case away from the
+// border and for moderate flow), the addresses are formed without clamps, edge rules and the final select -- about
+// a seventh fewer instructions.  Every lane of the warp must call it (__all_sync).
+template <typename F, int N>
+__device__ __forceinline__ void warp_address_n(int H, int W, int y, const int (&xc)[N], const float (&lu)[N],
+                                               const float (&lv)[N], WarpAddrT<F> (&t)[N]) {
+    const float magic = 12582912.0f;  // 1.5 * 2^23 (see warp_address_magic)
+    int sy[N], sx[N];
+    bool interior = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        sy[k] = y + (__float_as_int(__fadd_rd(lv[k], magic)) - 0x4B400000);
+        sx[k] = xc[k] + (__float_as_int(__fadd_rd(lu[k], magic)) - 0x4B400000);
+        interior &= ((unsigned)sy[k] < (unsigned)(H - 1)) & ((unsigned)sx[k] < (unsigned)(W - 1)) &
+                    (fabsf(lv[k]) < 4194304.0f) & (fabsf(lu[k]) < 4194304.0f);
+    }
+    if (__all_sync(0xffffffffu, interior)) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            t[k].fy = warp_fraction<F>(lv[k], __fadd_rd(lv[k], magic) - magic);
+            t[k].fx = warp_fraction<F>(lu[k], __fadd_rd(lu[k], magic) - magic);
+            t[k].inside = true;
+            t[k].o00 = (unsigned)(sy[k] * W + sx[k]);
+            t[k].o01 = t[k].o00 + 1u;
+            t[k].o10 = t[k].o00 + (unsigned)W;
+            t[k].o11 = t[k].o00 + (unsigned)W + 1u;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) warp_address_magic<F>(H, W, y, xc[k], lv[k], lu[k], t[k]);
+    }
+}
+
+// the loads of those samples into registers, all in flight together; one widening multiply-add per address
+// (IMAD.WIDE.U32) instead of a 64-bit add + shift pair
+template <typename F>
+__device__ __forceinline__ void warp_load_taps(const float* __restrict__ img, const WarpAddrT<F>& a, WarpTapT<F>& t) {
     const char* base = reinterpret_cast<const char*>(img);
-    t.v00 = __ldg(reinterpret_cast<const float*>(base + (size_t)o00 * 4u));
-    t.v01 = __ldg(reinterpret_cast<const float*>(base + (size_t)o01 * 4u));
-    t.v10 = __ldg(reinterpret_cast<const float*>(base + (size_t)(o00 + dy) * 4u));
-    t.v11 = __ldg(reinterpret_cast<const float*>(base + (size_t)(o01 + dy) * 4u));
+    t.fy = a.fy;
+    t.fx = a.fx;
+    t.inside = a.inside;
+    t.v00 = __ldg(reinterpret_cast<const float*>(base + (size_t)a.o00 * 4u));
+    t.v01 = __ldg(reinterpret_cast<const float*>(base + (size_t)a.o01 * 4u));
+    t.v10 = __ldg(reinterpret_cast<const float*>(base + (size_t)a.o10 * 4u));
+    t.v11 = __ldg(reinterpret_cast<const float*>(base + (size_t)a.o11 * 4u));
+}
+
+template <typename F>
+__device__ __forceinline__ void warp_gather_magic(const float* __restrict__ img, int H, int W, int yc, int xc, float v,
+                                                  float u, WarpTapT<F>& t) {
+    WarpAddrT<F> a;
+    warp_address_magic<F>(H, W, yc, xc, v, u, a);
+    warp_load_taps<F>(img, a, t);
+}
+
+template <typename F, int N>
+__device__ __forceinline__ void warp_gather_n(const float* __restrict__ img, int H, int W, int y, const int (&xc)[N],
+                                              const float (&lu)[N], const float (&lv)[N], WarpTapT<F> (&t)[N]) {
+    WarpAddrT<F> a[N];
+    warp_address_n<F, N>(H, W, y, xc, lu, lv, a);
+#pragma unroll
+    for (int k = 0; k < N; ++k) warp_load_taps<F>(img, a[k], t[k]);
 }
 
 template <typename F>
@@ -136,38 +206,11 @@ __global__ void __launch_bounds__(256) warp_rows_kernel(WarpRowsArgs a) {
             return;
         }
     }
-    // Integer / fraction split of every sample first; if the 2x2 taps of ALL samples of the warp lie
-    // strictly inside the frame (the common case away from the border and for moderate flow), the taps
-    // are fetched without clamps, edge rules and the final select -- about a seventh fewer instructions.
-    const float magic = 12582912.0f;  // 1.5 * 2^23 (see warp_gather_magic)
-    int sy[WR_PER_THREAD], sx[WR_PER_THREAD];
-    bool interior = true;
-#pragma unroll
-    for (int k = 0; k < WR_PER_THREAD; ++k) {
-        sy[k] = y + (__float_as_int(__fadd_rd(lv[k], magic)) - 0x4B400000);
-        sx[k] = min(x0 + 256 * k, W - 1) + (__float_as_int(__fadd_rd(lu[k], magic)) - 0x4B400000);
-        interior &= ((unsigned)sy[k] < (unsigned)(H - 1)) & ((unsigned)sx[k] < (unsigned)(W - 1)) &
-                    (fabsf(lv[k]) < 4194304.0f) & (fabsf(lu[k]) < 4194304.0f);
-    }
     WarpTapT<F> t[WR_PER_THREAD];
-    if (__all_sync(0xffffffffu, interior)) {
-        const char* base = reinterpret_cast<const char*>(img);
+    int xc[WR_PER_THREAD];
 #pragma unroll
-        for (int k = 0; k < WR_PER_THREAD; ++k) {
-            t[k].fy = warp_fraction<F>(lv[k], __fadd_rd(lv[k], magic) - magic);
-            t[k].fx = warp_fraction<F>(lu[k], __fadd_rd(lu[k], magic) - magic);
-            t[k].inside = true;
-            const unsigned o00 = (unsigned)(sy[k] * W + sx[k]);
-            t[k].v00 = __ldg(reinterpret_cast<const float*>(base + (size_t)o00 * 4u));
-            t[k].v01 = __ldg(reinterpret_cast<const float*>(base + (size_t)(o00 + 1u) * 4u));
-            t[k].v10 = __ldg(reinterpret_cast<const float*>(base + (size_t)(o00 + (unsigned)W) * 4u));
-            t[k].v11 = __ldg(reinterpret_cast<const float*>(base + (size_t)(o00 + (unsigned)W + 1u) * 4u));
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < WR_PER_THREAD; ++k)
-            warp_gather_magic<F>(img, H, W, y, min(x0 + 256 * k, W - 1), lv[k], lu[k], t[k]);
-    }
+    for (int k = 0; k < WR_PER_THREAD; ++k) xc[k] = min(x0 + 256 * k, W - 1);
+    warp_gather_n<F, WR_PER_THREAD>(img, H, W, y, xc, lu, lv, t);
 #pragma unroll
     for (int k = 0; k < WR_PER_THREAD; ++k) {
         const int x = x0 + 256 * k;

@@ -79,6 +79,11 @@ static inline void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int 
     if (__atomic_sub_fetch(&b->tx, bytes, __ATOMIC_SEQ_CST) == 0)  // the phase's last byte: complete it
         __atomic_store_n(&b->phase, b->phase ^ 1u, __ATOMIC_RELEASE);
 }
+// cp.async (LDGSTS): a synchronous 4-byte copy; groups complete at once
+static inline void cp_async4(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 4); }
+static inline void cp_async_commit() {}
+template <int PENDING>
+static inline void cp_async_wait() {}
 #define OF_FENCE_MBARRIER_INIT() __atomic_thread_fence(__ATOMIC_SEQ_CST)
 #define OF_KEEP_IN_REGISTER_F(x) (void)(x)
 #define OF_KEEP_ALIVE_L(x) (void)(x)
@@ -120,7 +125,7 @@ int emul_lk_march_u8(const uint8_t* prev, const uint8_t* curr, float* u, float* 
 int emul_lk_refine(int form, const float* prev, const float* curr, float* flow_u0, float* flow_v0, float* flow_u1,
                    float* flow_v1, int* sel, int sel_xor, int* done, double* partial, float* warped, unsigned* counter,
                    int* iters_executed, float* residuals, int max_iters, int iteration, int batch, int H, int W, int row_lo,
-                   int row_hi, int own_lo, int own_hi, int window) {
+                   int row_hi, int own_lo, int own_hi, int window, float* warped_next, int warped_ready) {
     RefineArgs ra;
     std::memset(&ra, 0, sizeof(ra));
     ra.prev = prev;
@@ -136,6 +141,8 @@ int emul_lk_refine(int form, const float* prev, const float* curr, float* flow_u
     ra.H = H;
     ra.W = W;
     ra.window = window;
+    ra.warped_next = warped_next;  // split forms: the marching kernel's epilogue warps the next iteration's input
+    ra.warped_ready = warped_ready;
     ra.row_lo = row_lo;
     ra.row_hi = row_hi;
     ra.own_lo = own_lo;

@@ -507,7 +507,7 @@ def emul_march(tmp_path_factory):
     lib.emul_lk_march.argtypes = [_vp] * 4 + [_i] * 5
     lib.emul_lk_march_u8.argtypes = [_vp] * 4 + [_i] * 4
     lib.emul_lk_march_fx.argtypes = [_vp] * 4 + [_i] * 4
-    lib.emul_lk_refine.argtypes = [_i] + [_vp] * 6 + [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 10
+    lib.emul_lk_refine.argtypes = [_i] + [_vp] * 6 + [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, _i]
     lib.emul_lk_refine_units_per_pair.argtypes = [_i, _i, _i]
     return lib
 
@@ -560,7 +560,8 @@ def test_marching_kernel_uint8_ingest_and_fixed_point_flavours(emul_march, shape
             assert np.array_equal(u16[b], uo) and np.array_equal(v16[b], vo), (quirk, b)
 
 
-def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state=None, rows=None, window=5):
+def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state=None, rows=None, window=5,
+                 warped=None, warped_next=None, warped_ready=0):
     b, h, w = prev.shape
     out_u, out_v = np.full_like(fu, 9.0), np.full_like(fv, 9.0)
     sel = np.zeros(b, np.int32) if state is None else state["sel"]
@@ -570,10 +571,11 @@ def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state
     lo, hi = rows if rows else (0, h)
     units = lib.emul_lk_refine_units_per_pair(b, hi - lo, w)  # the kernels index partial[pair][unit][2]
     partial = np.zeros((b, units, 2))
-    warped = np.zeros_like(prev)
+    warped = np.zeros_like(prev) if warped is None else warped
     cnt = np.zeros(b, np.uint32)
     rc = lib.emul_lk_refine(form, ptr(prev), ptr(curr), ptr(fu), ptr(fv), ptr(out_u), ptr(out_v), ptr(sel), 0, ptr(done),
-                            ptr(partial), ptr(warped), ptr(cnt), ptr(executed), ptr(resid), 4, iteration, b, h, w, lo, hi, lo, hi, window)
+                            ptr(partial), ptr(warped), ptr(cnt), ptr(executed), ptr(resid), 4, iteration, b, h, w, lo, hi, lo, hi, window,
+                            None if warped_next is None else ptr(warped_next), warped_ready)
     assert rc == 0
     return out_u, out_v, partial, dict(sel=sel, done=done, executed=executed, resid=resid)
 
@@ -605,6 +607,39 @@ def test_fast_refinement_iteration_source_on_cpu(emul_march, window):
     band_u, band_v, _, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, rows=(8, 30), window=window)
     assert np.array_equal(bits(band_u[:, 8:30]), bits(split_u[:, 8:30])) and np.array_equal(bits(band_v[:, 8:30]), bits(split_v[:, 8:30]))
     assert (band_u[:, :8] == 9.0).all() and (band_u[:, 30:] == 9.0).all()
+
+
+@pytest.mark.parametrize("window", [5, 7])
+def test_marching_kernel_warps_the_next_iteration_itself(emul_march, emul_warp, window):
+    """The refinement flavour's epilogue: warped_next = warp(curr, flow_out) from the flow the kernel has in registers
+    (asynchronous copies into a shared-memory landing zone, blended a step later).  It is warp_rows_kernel<float>'s
+    plane bit for bit -- on every row of the frame, with flow that leaves the frame, on a row band -- and a second
+    iteration that consumes it (no warp_rows launch) gives the classic two-launch iteration's bits."""
+    from scipy.ndimage import gaussian_filter
+
+    rng = np.random.default_rng(21)
+    b, h, w = 2, 43, 248
+    prev = gaussian_filter((rng.random((b, h, w)) * 255).astype(f32), (0, 1.5, 1.5)).astype(f32)
+    curr = np.roll(prev, (1, -1), axis=(1, 2)) + rng.standard_normal(prev.shape).astype(f32)
+    fu = (rng.standard_normal((b, h, w)) * 0.8).astype(f32)
+    fv = (rng.standard_normal((b, h, w)) * 0.8).astype(f32)
+    fu[0, :3, :5] = -7.5  # samples outside the frame
+    fv[1, -2:, -6:] = 9.25
+    # classic: iteration 1, then warp_rows + march for iteration 2
+    u1, v1, _, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, window=window)
+    u2, v2, part2, _ = _refine_once(emul_march, 0, prev, curr, u1, v1, window=window)
+    # chained: iteration 1 also writes the warped plane of iteration 2, which then launches no warp_rows
+    wn = np.full_like(prev, np.nan)
+    cu1, cv1, _, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, window=window, warped_next=wn)
+    assert np.array_equal(bits(cu1), bits(u1)) and np.array_equal(bits(cv1), bits(v1))
+    want = np.stack([run_warp(emul_warp, curr[k], u1[k], v1[k], exact=False) for k in range(b)])
+    assert np.array_equal(bits(wn), bits(want))
+    cu2, cv2, cpart2, _ = _refine_once(emul_march, 0, prev, curr, cu1, cv1, window=window, warped=wn, warped_ready=1)
+    assert np.array_equal(bits(cu2), bits(u2)) and np.array_equal(bits(cv2), bits(v2)) and np.array_equal(cpart2, part2)
+    # a row band: the plane is written on the band's rows only
+    wb = np.full_like(prev, 7.0)
+    _refine_once(emul_march, 0, prev, curr, fu, fv, window=window, rows=(8, 30), warped_next=wb)
+    assert np.array_equal(bits(wb[:, 8:30]), bits(want[:, 8:30])) and (wb[:, :8] == 7.0).all() and (wb[:, 30:] == 7.0).all()
 
 
 def test_fast_refinement_fused_tail_source_on_cpu(emul_march):
