@@ -288,13 +288,16 @@ bool refine_split() {
 #ifndef OF_EXACT_REFINE_SPLIT_DEFAULT
 #define OF_EXACT_REFINE_SPLIT_DEFAULT 1  // split passed the GPU suite (profiles/r01c_pytest_gpu_exact_v2.log)
 #endif
-// split refinement: the marching kernel warps the next iteration's input itself (default); OF_B200_REFINE_WARP=rows
-// keeps one warp_rows launch per iteration (A/B measurements)
+// split refinement, OF_B200_REFINE_WARP=chain: the marching kernel warps the next iteration's input itself (its
+// epilogue gathers through the flow it has in registers), so only a level's first iteration launches warp_rows.
+// Measured and NOT the default: the marching warps are latency-bound at 8 per SM, so every instruction added to them
+// costs its full latency -- 4 x 4K finest level: 308 us per iteration against 165 + 124 us for the two launches
+// (profiles/r02_refine_chain_*).  Kept behind the switch with its bit-equality test.
 bool refine_chain_warp() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("OF_B200_REFINE_WARP");
-        v = (e && std::string(e) == "rows") ? 0 : 1;
+        v = (e && std::string(e) == "chain") ? 1 : 0;
     }
     return v == 1;
 }
@@ -393,7 +396,7 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
         const bool fast_level = (mode == OF_MODE_FAST) && lk_refine_supported(ra, window);
         // split refinement: the marching kernel's last warp per pair also does the convergence step
         const bool fused_tail = fast_level && refine_split();
-        // ... and its epilogue warps the current frame through the flow it has just produced, so only the level's
+        // opt-in: its epilogue also warps the current frame through the flow it has just produced, so only the level's
         // first iteration launches warp_rows; the two warped planes alternate (bands run independently)
         const bool chain_warp = fused_tail && refine_chain_warp();
         for (int it = 0; it < iterations; ++it) {

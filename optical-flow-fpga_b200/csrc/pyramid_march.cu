@@ -32,6 +32,10 @@ namespace ofb {
 namespace {
 
 constexpr int PM_THREADS = 256;
+#ifndef OF_PM_MIN_CTAS
+#define OF_PM_MIN_CTAS 2
+#endif
+constexpr int PM_MIN_CTAS = OF_PM_MIN_CTAS;       // resident CTAs per SM the register budget is set for
 constexpr int PM_R = 8;                           // radius of the sigma = 2 kernel
 constexpr int PM_CH = 8;                          // fine rows per step
 constexpr int PM_OUTC = PM_THREADS - 2 * PM_R;    // 240 smoothed columns per strip
@@ -105,7 +109,7 @@ template <> struct PmPair<double> { typedef double2 type; };
 template <> struct PmPair<float> { typedef float2 type; };
 
 template <int FLAVOUR>
-__global__ void __launch_bounds__(PM_THREADS, 2) pyramid_march_kernel(const PyrMarchArgs a) {
+__global__ void __launch_bounds__(PM_THREADS, PM_MIN_CTAS) pyramid_march_kernel(const PyrMarchArgs a) {
     constexpr bool FMA = FLAVOUR != PM_EXACT;
     typedef typename std::conditional<FLAVOUR == PM_F32, float, double>::type A;  // accumulator / register type
     typedef typename PmPair<A>::type A2;
@@ -286,7 +290,7 @@ cudaError_t launch_pyramid_march(const float* src, float* dst, int batch, int H,
     // bands: CTAs run in waves of 148 SMs x 2 resident CTAs and every band recomputes 16 fine rows
     // (two steps) of filter warm-up; minimise  waves x (steps per band + 2)
     const int rows = row_hi - row_lo;
-    const long long per_band = (long long)batch * n_strips, slots = 148LL * 2;
+    const long long per_band = (long long)batch * n_strips, slots = 148LL * PM_MIN_CTAS;
     const int max_bands = (rows + 7) / 8;
     long long best_cost = -1;
     a.band_rows = rows;

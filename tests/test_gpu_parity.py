@@ -358,6 +358,37 @@ def test_exact_mode_kernel_variants_give_the_same_bits(ofb):
     assert len(set(got.values())) == 1, got
 
 
+def test_fast_mode_refinement_variants_give_the_same_bits(ofb):
+    """Fast mode's refinement iteration exists in three forms -- warp_rows + marching kernel (default), the marching
+    kernel warping the next iteration's input in its epilogue (OF_B200_REFINE_WARP=chain), and the kernel that
+    gathers inside the marching warps (OF_B200_REFINE=fused).  All three use the same sample and blend routines:
+    the pyramidal flow (window 5 and 7, early exits included) must hash identically."""
+    import os
+    import subprocess
+
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        f"sys.path.insert(0, {str(BACKEND_DIR)!r})\n"
+        "import of_b200\n"
+        "from scipy.ndimage import gaussian_filter, shift\n"
+        "rng = np.random.default_rng(78)\n"
+        "h = hashlib.sha256()\n"
+        "p = gaussian_filter((rng.random((3, 152, 248)) * 255).astype(np.float32), (0, 1.5, 1.5))\n"
+        "c = np.stack([shift(p[0], (-2.6, 3.4), order=1, mode='nearest'), shift(p[1], (1.2, -0.3), order=1, mode='nearest'), p[2]]).astype(np.float32)\n"
+        "for w, it in ((5, 4), (7, 3), (5, 1)):\n"
+        "    u, v = of_b200.lk_pyramidal_batch(p, c, 3, w, it, mode=of_b200.MODE_FAST)\n"
+        "    h.update(u.tobytes() + v.tobytes())\n"
+        "print(h.hexdigest())\n"
+    )
+    got = {}
+    for refine, warp in (("split", "rows"), ("split", "chain"), ("fused", "rows")):
+        env = dict(os.environ, OF_B200_REFINE=refine, OF_B200_REFINE_WARP=warp)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stderr[-2000:]
+        got[(refine, warp)] = res.stdout.strip().splitlines()[-1]
+    assert len(set(got.values())) == 1, got
+
+
 # ---------------------------------------------------------------------------------------
 # full-size frames: oracle on one pair + size-independent properties
 # ---------------------------------------------------------------------------------------
