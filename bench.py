@@ -67,8 +67,8 @@ WORKLOADS = {
     "pyramidal_4k_w7": dict(batch=16, H=2160, W=3840, pyramidal=True, levels=3, iters=3, window=7),
 }
 # measured next to the primary workload by a default run (the `workloads` map of the JSON line)
-DEFAULT_EXTRA = ["single_4k", "single_1080p_u8", "single_1080p_exact", "fixed_1080p", "pyramidal_4k", "pyramidal_4k_exact",
-                 "pyramidal_8k"]
+DEFAULT_EXTRA = ["single_4k", "single_1080p_u8", "single_1080p_exact", "fixed_1080p", "single_1080p_w7", "pyramidal_4k",
+                 "pyramidal_4k_exact", "pyramidal_4k_w7", "pyramidal_8k"]
 WINDOW = 5
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
@@ -682,7 +682,7 @@ def measure_workload(env: Env, name: str, wl: dict, steps: int, warmup: int, wan
     traffic, traffic_src = ncu_traffic_bytes(name, B)
     kernel = ("whole pyramidal step (all launches)" if wl["pyramidal"] else
               {"fixed": "lk_march_kernel<true, false, true, true> (uint8 in, S8.7 out)", "exact": "lk_exact_march_kernel<SRC_FRAMES>",
-               "u8": "lk_march_kernel<true, false, true> (uint8 frames)"}.get(variant, "lk_march_kernel<true, false> (one launch per step)"))
+               "u8": "lk_march_kernel<true, false, true> (uint8 frames)"}.get(variant, "lk_march_kernel<true, false, false, false, WIN = %d> (one launch per step)" % wl.get("window", WINDOW)))
     return {
         "name": name,
         "ms_per_step": ms_per_step,
