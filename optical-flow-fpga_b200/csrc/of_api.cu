@@ -285,6 +285,22 @@ bool refine_split() {
     return v == 1;
 }
 
+// OF_B200_REFINE=ws: the split form's marching kernel with producer warps that gather the warped rows into its ring
+// stages (lk_march_kernel<..., WS>): no warped plane, one launch per iteration.  Window 5; other windows stay split.
+bool refine_ws() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OF_B200_REFINE");
+        v = (e && std::string(e) == "ws") ? 1 : 0;
+    }
+    return v == 1;
+}
+cudaError_t launch_refine_split_form(const RefineArgs& ra, float* warped, int batch, int* launches, cudaStream_t stream) {
+    if (refine_ws() && ra.window == 5 && !ra.warped_ready && ra.warped_next == nullptr)
+        return launch_lk_refine_ws(ra, batch, launches, stream);
+    return launch_lk_refine_split(ra, warped, batch, launches, stream);
+}
+
 #ifndef OF_EXACT_REFINE_SPLIT_DEFAULT
 #define OF_EXACT_REFINE_SPLIT_DEFAULT 1  // split passed the GPU suite (profiles/r01c_pytest_gpu_exact_v2.log)
 #endif
@@ -415,11 +431,11 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                     ra.tail.residuals = resid_dev ? resid_dev + (size_t)ref_level * iterations * 2 : nullptr;
                     ra.tail.resid_pair_stride = (size_t)levels * iterations * 2;
                     ra.tail.iteration = it;
-                    OF_CUDA(launch_lk_refine_split(ra, warped_it, batch, &cnt.n, stream));
+                    OF_CUDA(launch_refine_split_form(ra, warped_it, batch, &cnt.n, stream));
                     continue;
                 }
                 if (refine_split())
-                    OF_CUDA(launch_lk_refine_split(ra, warped_it, batch, &cnt.n, stream));
+                    OF_CUDA(launch_refine_split_form(ra, warped_it, batch, &cnt.n, stream));
                 else
                     OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, stream));
             } else {
@@ -923,7 +939,7 @@ static int refine_dev_impl(const float* prev, const float* curr, float* flow_in_
     if (mode == OF_MODE_FAST && lk_refine_supported(ra, window)) {
         float* warped = reinterpret_cast<float*>(static_cast<char*>(workspace) + refine_partial_bytes(batch, height, width));
         if (refine_split())
-            OF_CUDA(launch_lk_refine_split(ra, warped, batch, &cnt.n, st));
+            OF_CUDA(launch_refine_split_form(ra, warped, batch, &cnt.n, st));
         else
             OF_CUDA(launch_lk_refine(ra, batch, &cnt.n, st));
         blocks = lk_refine_units_per_pair(batch, row_hi - row_lo, width);

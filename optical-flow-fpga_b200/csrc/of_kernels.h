@@ -145,6 +145,9 @@ cudaError_t launch_lk_refine(const RefineArgs& a, int batch, int* launches, cuda
 // Split form of the same iteration: warp_rows (gather the current frame through the flow into
 // `warped`, rows [row_lo - 3, row_hi + 3)) followed by the K1 marching kernel in REFINE mode.
 cudaError_t launch_lk_refine_split(const RefineArgs& a, float* warped, int batch, int* launches, cudaStream_t stream);
+// Warp-specialised form (window 5): producer warps gather the warped rows into the marching warps' ring stages; no
+// warped plane, one launch.  Same bits as the split form; honours a.tail like it.
+cudaError_t launch_lk_refine_ws(const RefineArgs& a, int batch, int* launches, cudaStream_t stream);
 // The warp alone: warped[pair][y][x] = bilinear(curr, y + v, x + u) for rows [row_lo, row_hi) of every pair
 // that has not converged, flow = the current ping-pong buffer of `a`.  exact = float64 sample fractions
 // (warp_image's bits for any flow); false = the float32 fractions of the fast path.

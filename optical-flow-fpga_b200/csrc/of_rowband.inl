@@ -356,12 +356,12 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
                     ra.tail.residuals = resid + (size_t)ref_level * (iters > 0 ? iters : 1) * 2;
                     ra.tail.resid_pair_stride = 0;
                     ra.tail.iteration = it;
-                    OF_CUDA(launch_lk_refine_split(ra, F(c.warped_off), 1, &cnt.n, st));
+                    OF_CUDA(launch_refine_split_form(ra, F(c.warped_off), 1, &cnt.n, st));
                     continue;
                 }
                 if (fast_level) {
                     if (refine_split())
-                        OF_CUDA(launch_lk_refine_split(ra, F(c.warped_off), 1, &cnt.n, st));
+                        OF_CUDA(launch_refine_split_form(ra, F(c.warped_off), 1, &cnt.n, st));
                     else
                         OF_CUDA(launch_lk_refine(ra, 1, &cnt.n, st));
                     blocks = lk_refine_units_per_pair(1, hi - lo, w);

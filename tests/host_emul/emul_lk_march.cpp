@@ -43,23 +43,51 @@ static inline uint32_t smem_u32(const void* p) {
 }
 static inline char* smem_ptr(uint32_t a) { return static_cast<char*>(cuda_on_host::dynamic_smem()) + (a - 128u); }
 struct HostBarrier {
-    int tx;          // bytes still expected in the current phase
-    unsigned phase;  // parity of the current (incomplete) phase
+    int tx;                  // bytes still expected in the current phase
+    unsigned short pending;  // arrivals still expected in the current phase
+    unsigned char count;     // arrivals per phase
+    unsigned char phase;     // parity of the current (incomplete) phase
 };
 static_assert(sizeof(HostBarrier) == 8, "an mbarrier is 8 bytes");
-static inline void mbar_init(uint32_t bar, uint32_t) {
+static pthread_mutex_t g_mbar_lock = PTHREAD_MUTEX_INITIALIZER;  // one lock for every barrier: speed is no concern here
+static inline void mbar_complete_if_done(HostBarrier* b) {       // lock held
+    if (b->pending == 0 && b->tx == 0) {
+        b->pending = b->count;
+        __atomic_store_n(&b->phase, (unsigned char)(b->phase ^ 1u), __ATOMIC_RELEASE);
+    }
+}
+static inline void mbar_init(uint32_t bar, uint32_t count) {
     HostBarrier* b = reinterpret_cast<HostBarrier*>(smem_ptr(bar));
     b->tx = 0;
+    b->pending = (unsigned short)count;
+    b->count = (unsigned char)count;
     b->phase = 0;
 }
+// mbarrier.arrive.expect_tx: one arrival that also announces `bytes`
 static inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    __atomic_fetch_add(&reinterpret_cast<HostBarrier*>(smem_ptr(bar))->tx, (int)bytes, __ATOMIC_SEQ_CST);
+    HostBarrier* b = reinterpret_cast<HostBarrier*>(smem_ptr(bar));
+    pthread_mutex_lock(&g_mbar_lock);
+    b->tx += (int)bytes;
+    b->pending -= 1;
+    mbar_complete_if_done(b);
+    pthread_mutex_unlock(&g_mbar_lock);
+}
+static inline void mbar_arrive(uint32_t bar) {
+    HostBarrier* b = reinterpret_cast<HostBarrier*>(smem_ptr(bar));
+    pthread_mutex_lock(&g_mbar_lock);
+    b->pending -= 1;
+    mbar_complete_if_done(b);
+    pthread_mutex_unlock(&g_mbar_lock);
 }
 static inline bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     const bool done = __atomic_load_n(&reinterpret_cast<HostBarrier*>(smem_ptr(bar))->phase, __ATOMIC_ACQUIRE) != parity;
     if (!done) sched_yield();
     return done;
 }
+template <int REGS>
+static inline void setmaxnreg_inc() {}
+template <int REGS>
+static inline void setmaxnreg_dec() {}
 static inline void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
     HostTensorMap m;
     std::memcpy(&m, map, sizeof(m));
@@ -76,8 +104,10 @@ static inline void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int 
         }
     HostBarrier* b = reinterpret_cast<HostBarrier*>(smem_ptr(bar));
     const int bytes = m.box_h * m.box_w * m.elem;
-    if (__atomic_sub_fetch(&b->tx, bytes, __ATOMIC_SEQ_CST) == 0)  // the phase's last byte: complete it
-        __atomic_store_n(&b->phase, b->phase ^ 1u, __ATOMIC_RELEASE);
+    pthread_mutex_lock(&g_mbar_lock);
+    b->tx -= bytes;  // complete_tx; the phase's last byte (and arrival) completes it
+    mbar_complete_if_done(b);
+    pthread_mutex_unlock(&g_mbar_lock);
 }
 // cp.async (LDGSTS): a synchronous 4-byte copy; groups complete at once
 static inline void cp_async4(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 4); }
@@ -148,7 +178,7 @@ int emul_lk_refine(int form, const float* prev, const float* curr, float* flow_u
     ra.own_lo = own_lo;
     ra.own_hi = own_hi;
     if (!lk_refine_supported(ra, window)) return -1;
-    if (form == 1) {
+    if (form == 1 || form == 4) {
         ra.tail.counter = counter;
         ra.tail.peers = 0;
         ra.tail.n_pixels = (double)H * (double)W;
@@ -161,6 +191,7 @@ int emul_lk_refine(int form, const float* prev, const float* curr, float* flow_u
         ra.tail.iteration = iteration;
     }
     if (form == 2) return (int)launch_lk_refine(ra, batch, nullptr, nullptr);
+    if (form == 3 || form == 4) return (int)launch_lk_refine_ws(ra, batch, nullptr, nullptr);  // 4: with the fused tail
     return (int)launch_lk_refine_split(ra, warped, batch, nullptr, nullptr);
 }
 int emul_lk_refine_units_per_pair(int batch, int rows, int W) { return lk_refine_units_per_pair(batch, rows, W); }

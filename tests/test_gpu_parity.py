@@ -359,9 +359,10 @@ def test_exact_mode_kernel_variants_give_the_same_bits(ofb):
 
 
 def test_fast_mode_refinement_variants_give_the_same_bits(ofb):
-    """Fast mode's refinement iteration exists in three forms -- warp_rows + marching kernel (default), the marching
-    kernel warping the next iteration's input in its epilogue (OF_B200_REFINE_WARP=chain), and the kernel that
-    gathers inside the marching warps (OF_B200_REFINE=fused).  All three use the same sample and blend routines:
+    """Fast mode's refinement iteration exists in four forms -- warp_rows + marching kernel, the marching
+    kernel warping the next iteration's input in its epilogue (OF_B200_REFINE_WARP=chain), the kernel that
+    gathers inside the marching warps (OF_B200_REFINE=fused), and the warp-specialised marching kernel whose producer
+    warps fill the ring stages (OF_B200_REFINE=ws).  All use the same sample and blend routines:
     the pyramidal flow (window 5 and 7, early exits included) must hash identically."""
     import os
     import subprocess
@@ -381,9 +382,9 @@ def test_fast_mode_refinement_variants_give_the_same_bits(ofb):
         "print(h.hexdigest())\n"
     )
     got = {}
-    for refine, warp in (("split", "rows"), ("split", "chain"), ("fused", "rows")):
+    for refine, warp in (("split", "rows"), ("split", "chain"), ("fused", "rows"), ("ws", "rows")):
         env = dict(os.environ, OF_B200_REFINE=refine, OF_B200_REFINE_WARP=warp)
-        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, res.stderr[-2000:]
         got[(refine, warp)] = res.stdout.strip().splitlines()[-1]
     assert len(set(got.values())) == 1, got

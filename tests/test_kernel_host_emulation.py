@@ -596,6 +596,14 @@ def test_fast_refinement_iteration_source_on_cpu(emul_march, window):
     split_u, split_v, split_part, _ = _refine_once(emul_march, 0, prev, curr, fu, fv, window=window)
     fused_u, fused_v, fused_part, _ = _refine_once(emul_march, 2, prev, curr, fu, fv, window=window)
     assert np.array_equal(bits(split_u), bits(fused_u)) and np.array_equal(bits(split_v), bits(fused_v))
+    if window == 5:
+        # the warp-specialised form (producer warps fill the marching warps' ring stages: no warped plane) -- same bits,
+        # same per-unit sums as the split form
+        ws_u, ws_v, ws_part, _ = _refine_once(emul_march, 3, prev, curr, fu, fv, window=window)
+        assert np.array_equal(bits(split_u), bits(ws_u)) and np.array_equal(bits(split_v), bits(ws_v))
+        assert np.array_equal(ws_part, split_part)
+        wb_u, wb_v, _, _ = _refine_once(emul_march, 3, prev, curr, fu, fv, rows=(8, 30), window=window)
+        assert np.array_equal(bits(wb_u[:, 8:30]), bits(split_u[:, 8:30])) and (wb_u[:, :8] == 9.0).all() and (wb_u[:, 30:] == 9.0).all()
     # the sums of |du|, |dv| are formed differently (four float32 magnitudes are added before widening in one form)
     assert split_part.sum(axis=1) == pytest.approx(fused_part.sum(axis=1), rel=1e-8)
     for k in range(b):
@@ -653,6 +661,9 @@ def test_fast_refinement_fused_tail_source_on_cpu(emul_march):
     zeros = np.zeros_like(prev)
     out_u, out_v, _, st = _refine_once(emul_march, 1, prev, curr, zeros, zeros.copy())
     assert st["sel"].tolist() == [1, 1] and st["done"].tolist() == [0, 1] and st["executed"].tolist() == [1, 1]
+    ws_u, ws_v, _, ws_st = _refine_once(emul_march, 4, prev, curr, zeros, zeros.copy())  # warp-specialised form, same tail
+    assert np.array_equal(bits(ws_u), bits(out_u)) and np.array_equal(bits(ws_v), bits(out_v))
+    assert ws_st["sel"].tolist() == [1, 1] and ws_st["done"].tolist() == [0, 1] and np.array_equal(ws_st["resid"], st["resid"])
     du, dv = orc.lucas_kanade_single_scale(prev[0], curr[0], 5)  # flow_in = 0: the warp is the identity
     assert np.array_equal(bits(out_u[0]), bits(du)) and np.array_equal(bits(out_v[0]), bits(dv))
     assert st["resid"][0, 0, 0] == pytest.approx(np.abs(du).mean(), rel=1e-5)
