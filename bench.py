@@ -259,7 +259,8 @@ def reference_arm(args, wl, rank: int, world: int):
         t0 = time.perf_counter()
         run_oracle_sample(pool, cores, wl, calib_rows, cores, 1000)
         calib = time.perf_counter() - t0
-        budget = 120.0 / max(1, steps + warmup)
+        # OF_BENCH_REF_BUDGET_S: total CPU time the arm aims at (tests shrink it)
+        budget = float(os.environ.get("OF_BENCH_REF_BUDGET_S", "120")) / max(1, steps + warmup)
         rows = int(calib_rows * budget / max(calib, 1e-3))
         rows = max(32, min(wl["H"], rows))
         rows -= rows % 8
