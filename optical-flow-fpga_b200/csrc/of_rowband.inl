@@ -18,7 +18,13 @@
 
 namespace {
 
-constexpr int RB_GROW = 4;
+// Rows by which a band's computed range shrinks per iteration: an iteration reads flow_in window_size / 2 + 1 rows
+// beyond the rows it writes, one more row is left for the even alignment of the band start, rounded up to even
+// (4 for windows up to 5, 6 for window 7).  distributed.py's band_grow is the same rule.
+inline int rb_grow(int window) {
+    const int g = (window / 2 + 2 + 1) & ~1;
+    return g < 4 ? 4 : g;
+}
 
 struct RowbandCtx {
     int rank = 0, world = 1, H = 0, W = 0, L = 1, window = 5, iters = 3, mode = OF_MODE_FAST;
@@ -79,7 +85,6 @@ int of_rowband_create(of_rowband_t** out, int rank, int world, int height, int w
     if (height < 1 || width < 1 || (long long)height * width > (1LL << 31) - 1)
         return fail(OF_ERR_INVALID_ARGUMENT, "bad frame size");
     OF_TRY(check_window(window));
-    if (window / 2 + 1 > RB_GROW - 1) return fail(OF_ERR_UNSUPPORTED, "row-band mode supports window_size <= 5");
     if (mode != OF_MODE_EXACT && mode != OF_MODE_FAST) return fail(OF_ERR_INVALID_ARGUMENT, "unknown mode");
     if (iterations < 0 || iterations > 1000) return fail(OF_ERR_INVALID_ARGUMENT, "num_iterations must be in 0..1000");
     if (levels < 1 || levels > 16) return fail(OF_ERR_INVALID_ARGUMENT, "num_levels must be in 1..16");
@@ -307,7 +312,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         int* sel_k = sel + k;
         int* done_k = done + k;
         if (k < kc && b > a) {
-            const int reach = RB_GROW * (iters > 1 ? iters : 1) + RB_GROW;
+            const int reach = rb_grow(c.window) * (iters > 1 ? iters : 1) + rb_grow(c.window);
             const int lo = a - reach < 0 ? 0 : a - reach, hi = b + reach > h ? h : b + reach;
             if (replicated(k + 1))  // the coarser level lives whole in this rank's ping-pong buffers
                 OF_CUDA(launch_upsample_flow(fu(k + 1, 0), fv(k + 1, 0), fu(k + 1, 1), fv(k + 1, 1), sel + (k + 1), start,
@@ -335,7 +340,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
         ra.own_hi = b;
         const bool fast_level = (c.mode == OF_MODE_FAST) && lk_refine_supported(ra, c.window);
         for (int it = 0; it < iters; ++it) {
-            const int ext = RB_GROW * (iters - 1 - it);
+            const int ext = rb_grow(c.window) * (iters - 1 - it);
             int lo = a - ext < 0 ? 0 : a - ext;
             lo -= lo & 1;  // even start: rows pair up identically on every rank
             const int hi = b + ext > h ? h : b + ext;
@@ -429,7 +434,7 @@ int of_rowband_run(of_rowband_t* ctx, const float* prev, const float* curr, floa
             size_t lo_el[PEER_MAX_WORLD], hi_el[PEER_MAX_WORLD];
             const int hf = c.h[k - 1];
             const double sy = hf > 1 ? (double)(h - 1) / (double)(hf - 1) : 0.0;  // np.linspace step of upsample_flow
-            const int reach = RB_GROW * (iters > 1 ? iters : 1) + RB_GROW;
+            const int reach = rb_grow(c.window) * (iters > 1 ? iters : 1) + rb_grow(c.window);
             for (int r = 0; r < PEER_MAX_WORLD; ++r) {
                 lo_el[r] = hi_el[r] = 0;
                 if (r >= world) continue;

@@ -137,8 +137,9 @@ def lk_single_scale_rowbands(
 #
 # Every rank keeps full-size level images and flow planes but computes only its band of rows.
 # Inside a level there is NO halo exchange: iteration i of I is computed on the band extended
-# by GROW * (I - 1 - i) rows on both sides (a refinement iteration reads flow_in 3 rows beyond
-# the rows it writes; GROW = 4 leaves one row for the even alignment of the band start), so
+# by band_grow(window) * (I - 1 - i) rows on both sides (a refinement iteration reads flow_in
+# window // 2 + 1 rows beyond the rows it writes; one more row is left for the even alignment of the
+# band start, rounded up to even: 4 rows for windows up to 5, 6 for window 7), so
 # after the last iteration exactly the owned rows are still valid.  Communication happens
 #   * once per iteration: all-reduce of (sum|du|, sum|dv|) over the owned rows -- 16 bytes,
 #     needed for the reference's global early exit (lucas_kanade_pyramidal.py:213-223);
@@ -151,7 +152,9 @@ def lk_single_scale_rowbands(
 # Backends: `CudaBackend` (torch CUDA tensors + the `_dev` C-ABI calls) is the product path;
 # the split / collective logic is backend-agnostic so that tests can drive it on CPU tensors.
 
-GROW = 4
+def band_grow(window_size: int) -> int:
+    """Rows by which a band's computed range shrinks per iteration (csrc/of_rowband.inl: rb_grow)."""
+    return max(4, (window_size // 2 + 3) & ~1)
 
 
 class SingleProcessComm:
@@ -344,9 +347,7 @@ def lk_pyramidal_rowbands(
         mode = of_b200.default_mode()
     rank, world = comm.rank, comm.world
     backend.mode = mode  # the fast drivers' pyramid uses the fast filter (same bits as the single-GPU fast path)
-    halo = window_size // 2 + 1
-    if halo > GROW - 1:
-        raise ValueError("row-band mode supports window_size <= 5")
+    GROW = band_grow(int(window_size))
     iters = int(num_iterations)
 
     def gather(arr, h):

@@ -165,12 +165,12 @@ def _pyr_thread(rank, comm, out, args):
     sys.path.insert(0, str(BACKEND_DIR))
     import distributed as ofd
 
-    p, c, levels, iters = args
-    out[rank] = ofd.lk_pyramidal_rowbands(p, c, levels, 5, iters, mode=0, comm=comm.view(rank), backend=OracleBackend())
+    p, c, levels, iters, window = args
+    out[rank] = ofd.lk_pyramidal_rowbands(p, c, levels, window, iters, mode=0, comm=comm.view(rank), backend=OracleBackend())
 
 
-@pytest.mark.parametrize("world,levels,iters", [(3, 3, 3), (2, 2, 1), (4, 3, 2)])
-def test_pyramidal_rowbands_thread_ranks_equal_oracle(world, levels, iters):
+@pytest.mark.parametrize("world,levels,iters,window", [(3, 3, 3, 5), (2, 2, 1, 5), (4, 3, 2, 5), (3, 3, 3, 7), (4, 2, 2, 3)])
+def test_pyramidal_rowbands_thread_ranks_equal_oracle(world, levels, iters, window):
     import threading
 
     sys.path.insert(0, str(BACKEND_DIR))
@@ -178,10 +178,10 @@ def test_pyramidal_rowbands_thread_ranks_equal_oracle(world, levels, iters):
     from oracle import lk_float_oracle as orc
 
     p, c = _pyr_case()
-    uo, vo = orc.lucas_kanade_pyramidal(p, c, levels, 5, iters)
+    uo, vo = orc.lucas_kanade_pyramidal(p, c, levels, window, iters)
     comm = ofd.ThreadComm(world)
     out = [None] * world
-    threads = [threading.Thread(target=_pyr_thread, args=(r, comm, out, (p, c, levels, iters))) for r in range(world)]
+    threads = [threading.Thread(target=_pyr_thread, args=(r, comm, out, (p, c, levels, iters, window))) for r in range(world)]
     for t in threads:
         t.start()
     for t in threads:

@@ -483,20 +483,22 @@ def test_error_behaviour(ofb):
 def _rowband_thread(rank, comm, out, args):
     import distributed as ofd
 
-    p, c, levels, iters, mode = args
+    p, c, levels, iters, mode = args[:5]
+    window = args[5] if len(args) > 5 else 5
     try:
-        out[rank] = ofd.lk_pyramidal_rowbands(p, c, levels, 5, iters, mode=mode, comm=comm.view(rank),
+        out[rank] = ofd.lk_pyramidal_rowbands(p, c, levels, window, iters, mode=mode, comm=comm.view(rank),
                                               backend=ofd.CudaBackend())
     except Exception as e:  # surface the failure in the main thread
         out[rank] = e
         comm._barrier.abort()
 
 
+@pytest.mark.parametrize("window", [5, 7])
 @pytest.mark.parametrize("mode_name", ["exact", "fast"])
 @pytest.mark.parametrize("world", [1, 3])
-def test_pyramidal_rowbands_equal_single_gpu(ofb, world, mode_name):
-    """Each rank computes only its rows (plus the shrinking overlap); the gathered result must
-    equal the whole-frame run bit for bit, in both arithmetic modes."""
+def test_pyramidal_rowbands_equal_single_gpu(ofb, world, mode_name, window):
+    """Each rank computes only its rows (plus the shrinking overlap: 4 rows per iteration for window 5, 6 for
+    window 7); the gathered result must equal the whole-frame run bit for bit, in both arithmetic modes."""
     import threading
 
     import distributed as ofd
@@ -505,22 +507,22 @@ def test_pyramidal_rowbands_equal_single_gpu(ofb, world, mode_name):
     mode = ofb.MODE_EXACT if mode_name == "exact" else ofb.MODE_FAST
     prev, curr, _ = synthetic.make_pairs_numpy(1, 200, 248, seed=31)
     p, c = prev[0], np.roll(curr[0], 3, axis=0)  # large enough motion for several iterations
-    u1, v1, (iters_exec, _) = ofb.lk_pyramidal(p, c, 3, 5, 3, mode=mode, return_trace=True)
+    u1, v1, (iters_exec, _) = ofb.lk_pyramidal(p, c, 3, window, 3, mode=mode, return_trace=True)
     if world == 1:
-        u, v = ofd.lk_pyramidal_rowbands(p, c, 3, 5, 3, mode=mode, comm=ofd.SingleProcessComm(), backend=ofd.CudaBackend())
+        u, v = ofd.lk_pyramidal_rowbands(p, c, 3, window, 3, mode=mode, comm=ofd.SingleProcessComm(), backend=ofd.CudaBackend())
         results = [(u, v)]
     else:
         comm = ofd.ThreadComm(world)
         results = [None] * world
-        ts = [threading.Thread(target=_rowband_thread, args=(r, comm, results, (p, c, 3, 3, mode))) for r in range(world)]
+        ts = [threading.Thread(target=_rowband_thread, args=(r, comm, results, (p, c, 3, 3, mode, window))) for r in range(world)]
         for t in ts:
             t.start()
         for t in ts:
             t.join()
     for r, res in enumerate(results):
         assert not isinstance(res, Exception), res
-        assert_bit_equal(res[0], u1, f"rank {r} u ({mode_name})")
-        assert_bit_equal(res[1], v1, f"rank {r} v ({mode_name})")
+        assert_bit_equal(res[0], u1, f"rank {r} u ({mode_name}, window {window})")
+        assert_bit_equal(res[1], v1, f"rank {r} v ({mode_name}, window {window})")
 
 
 def test_device_building_blocks_match_host_entry_points(ofb, golden_units):
@@ -711,10 +713,11 @@ def test_gpu_flow_metrics_against_reference_baseline(ofb, golden_index, golden_f
 
 
 @pytest.mark.parametrize("mode_name", ["exact", "fast"])
-@pytest.mark.parametrize("world,shape,levels,iters,repl_px", [(1, (200, 248), 3, 3, 0), (3, (200, 248), 3, 3, 0),
-                                                              (4, (270, 480), 4, 4, 0), (4, (270, 480), 4, 4, 10000),
-                                                              (3, (200, 248), 3, 3, 10 ** 9), (8, (96, 128), 2, 2, 0)])
-def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iters, repl_px, mode_name):
+@pytest.mark.parametrize("world,shape,levels,iters,repl_px,window",
+                         [(1, (200, 248), 3, 3, 0, 5), (3, (200, 248), 3, 3, 0, 5), (4, (270, 480), 4, 4, 0, 5),
+                          (4, (270, 480), 4, 4, 10000, 5), (3, (200, 248), 3, 3, 10 ** 9, 5), (8, (96, 128), 2, 2, 0, 5),
+                          (3, (200, 248), 3, 3, 0, 7), (4, (270, 480), 4, 4, 10000, 7)])
+def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iters, repl_px, window, mode_name):
     """of_rowband_run: `world` ranks emulated on ONE device, each with its own arena and stream;
     the peer "mapping" is the other contexts' arena pointers.  Every call only enqueues, so one
     host thread can issue all ranks; the ranks' kernels then meet through the flag words exactly as
@@ -728,10 +731,10 @@ def test_native_rowband_driver_equals_single_gpu(ofb, world, shape, levels, iter
     H, W = shape
     prev, curr, _ = synthetic.make_pairs_numpy(1, H, W, seed=31)
     p, c = prev[0], np.roll(curr[0], 3, axis=0)
-    u1, v1, (iters_exec, _) = ofb.lk_pyramidal(p, c, levels, 5, iters, mode=mode, return_trace=True)
+    u1, v1, (iters_exec, _) = ofb.lk_pyramidal(p, c, levels, window, iters, mode=mode, return_trace=True)
     dev = torch.device("cuda", 0)
     pd, cd = torch.from_numpy(p).to(dev), torch.from_numpy(c).to(dev)
-    ctxs = [ofb.RowbandContext(r, world, H, W, levels, 5, iters, mode) for r in range(world)]
+    ctxs = [ofb.RowbandContext(r, world, H, W, levels, window, iters, mode) for r in range(world)]
     try:
         arenas = [cx.arena_ptr for cx in ctxs]
         for cx in ctxs:
