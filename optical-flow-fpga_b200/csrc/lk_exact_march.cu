@@ -30,6 +30,7 @@
 #include "of_common.cuh"
 #include "f32x2.cuh"
 #include "of_kernels.h"
+#include "peer_device.cuh"
 
 namespace ofb {
 namespace {
@@ -370,6 +371,19 @@ __global__ void __launch_bounds__(XM_WARPS * 32, XM_UNITS_PER_SM) lk_exact_march
                 part[2 * s_ + 0] = 0.0;
                 part[2 * s_ + 1] = 0.0;
             }
+        }
+        if (a.tail.counter != nullptr && warp == 0) {
+            // fused tail of the iteration (peer_device.cuh): the pair's last unit reduces the units' partials in a
+            // fixed order and applies the reference's convergence test -- no iter_finalize launch
+            unsigned ticket = 0;
+            if (lane == 0) {
+                __threadfence();
+                ticket = atomicAdd(a.tail.counter + pair, 1u);
+            }
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            const int units_per_pair = xa.n_bands * xa.n_pairs_of_strips;
+            if (ticket == (unsigned)units_per_pair - 1u)
+                warp_iteration_tail(a.tail, a.partial + (size_t)pair * xa.slots_per_pair * 2, units_per_pair, pair, lane);
         }
     }
 }

@@ -454,11 +454,17 @@ static bool exact_march() {
     return v == 1;
 }
 
+static bool takes_exact_march(int src, int window, const TileArgs& a) {
+    return window == 5 && (src == SRC_FRAMES || src == SRC_WARPED) && (size_t)a.H * a.W < ((size_t)1 << 31) && exact_march();
+}
+
+bool lk_tile_fuses_tail(int src, int window, const TileArgs& a) { return src == SRC_WARPED && takes_exact_march(src, window, a); }
+
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream) {
     if (batch > 65535) return cudaErrorInvalidValue;
+    if (a.tail.counter != nullptr && !lk_tile_fuses_tail(src, window, a)) return cudaErrorInvalidValue;  // nobody would run it
     if (launches) *launches += 1;
-    if (window == 5 && (src == SRC_FRAMES || src == SRC_WARPED) && (size_t)a.H * a.W < ((size_t)1 << 31) && exact_march())
-        return launch_lk_exact_march(src, a, batch, stream);
+    if (takes_exact_march(src, window, a)) return launch_lk_exact_march(src, a, batch, stream);
     if (window == 5 && (src == SRC_FRAMES || src == SRC_WARPED) && (size_t)a.H * a.W < ((size_t)1 << 31) && tile_v2())
         return launch_lk_tile5(src, a, batch, stream);
     switch (src) {

@@ -462,7 +462,23 @@ int pyramidal_dev(const float* prev, const float* curr, float* u, float* v, int 
                     // kernel reads it like a frame: its replicated border is the warp at the clamped pixel
                     OF_CUDA(launch_warp_rows(ra, F(p.warped_off[k]), 0, p.h[k], true, batch, &cnt.n, stream));
                     a.in1 = F(p.warped_off[k]);
+                    // the marching exact kernel finishes the iteration itself (its pair's last unit reduces the
+                    // partial sums and applies the convergence test): no iter_finalize launch
+                    const bool tile_tail = lk_tile_fuses_tail(SRC_WARPED, window, a);
+                    if (tile_tail) {
+                        a.tail.counter = reinterpret_cast<unsigned*>(ws + p.cnt_off);
+                        a.tail.peers = 0;
+                        a.tail.n_pixels = (double)p.h[k] * (double)p.w[k];
+                        a.tail.sel = sel_k;
+                        a.tail.done = done_k;
+                        a.tail.iters_executed = iters_dev ? iters_dev + ref_level : nullptr;
+                        a.tail.iters_pair_stride = levels;
+                        a.tail.residuals = resid_dev ? resid_dev + (size_t)ref_level * iterations * 2 : nullptr;
+                        a.tail.resid_pair_stride = (size_t)levels * iterations * 2;
+                        a.tail.iteration = it;
+                    }
                     OF_CUDA(launch_lk_tile(SRC_WARPED, window, a, batch, &cnt.n, stream));
+                    if (tile_tail) continue;
                 } else {
                     OF_CUDA(launch_lk_tile(SRC_WARP, window, a, batch, &cnt.n, stream));
                 }

@@ -175,7 +175,12 @@ struct TileArgs {
     float* out_v;
     int H, W;
     int row_lo, row_hi, own_lo, own_hi;  // SRC_WARP row-band mode (see RefineArgs); else 0, H, 0, H
+    // SRC_WARPED on the marching exact kernel only (lk_tile_fuses_tail): counter != nullptr -> the pair's last unit
+    // finishes the iteration itself (convergence test, ping-pong flip, trace) and no iter_finalize launch follows
+    IterTail tail;
 };
+// whether launch_lk_tile(src, window, a, ...) runs a kernel that honours a.tail (the marching exact kernel)
+bool lk_tile_fuses_tail(int src, int window, const TileArgs& a);
 cudaError_t launch_lk_tile(int src, int window, const TileArgs& a, int batch, int* launches, cudaStream_t stream);
 // window 5, SRC_FRAMES / SRC_WARPED: second version of the kernel (lk_tile5.cu); called through launch_lk_tile
 cudaError_t launch_lk_tile5(int src, const TileArgs& a, int batch, cudaStream_t stream);

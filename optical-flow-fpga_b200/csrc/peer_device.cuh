@@ -95,4 +95,31 @@ __device__ __forceinline__ void apply_convergence(const IterTail& t, int pair, d
     if (mu < OF_CONVERGENCE_EPS && mv < OF_CONVERGENCE_EPS) t.done[pair] = 1;
 }
 
+// Fused tail of a refinement iteration.  Every unit of a pair stores its partial sums, fences and takes a ticket from
+// the pair's counter; the unit that draws the last ticket (every other unit's partial is then visible) calls this with
+// ONE full warp: the n_units partials are reduced in a fixed order -- whichever unit it is --, all-reduced over the
+// ranks if the level is split, and the reference's convergence test is applied.  Saves a launch per iteration.
+__device__ __forceinline__ void warp_iteration_tail(const IterTail& t, const double* part, int n_units, int pair, int lane) {
+    __threadfence();
+    double su = 0.0, sv = 0.0;
+    for (int i = lane; i < n_units; i += 32) {
+        su += __ldcg(part + 2 * i);
+        sv += __ldcg(part + 2 * i + 1);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        su += __shfl_down_sync(0xffffffffu, su, off);
+        sv += __shfl_down_sync(0xffffffffu, sv, off);
+    }
+    su = __shfl_sync(0xffffffffu, su, 0);
+    sv = __shfl_sync(0xffffffffu, sv, 0);
+    double tu = su, tv = sv;
+    bool ok = true;
+    if (t.peers) warp_peer_allreduce(t.sync, su, sv, tu, tv, ok);
+    if (lane == 0) {
+        t.counter[pair] = 0;  // ready for the next launch
+        apply_convergence(t, pair, tu, tv, ok);
+    }
+}
+
 }  // namespace ofb

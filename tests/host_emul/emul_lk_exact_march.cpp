@@ -3,6 +3,7 @@
 // below and compiled by g++ on top of cuda_on_host.h (CUDA threads = OS threads, __syncwarp a barrier, packed pairs
 // two IEEE operations).  TEST INFRASTRUCTURE; tests/test_kernel_host_emulation.py builds and drives it.
 #include "cuda_on_host.h"
+#include "peer_on_host.h"  // the fused iteration tail (peer_device.cuh)
 
 #include "lk_exact_march.cu"
 

@@ -123,16 +123,9 @@ static inline void cp_async_wait() {}
 static inline float rcp_approx(float x) { volatile float r = 1.0f / x; return r; }
 static inline double rcp_approx_f64(double x) { volatile double r = 1.0 / x; return r; }
 
-// ---- peer_device.cuh's system-scope flag accesses ----------------------------------------------------------------
-static inline void st_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-static inline unsigned long long ld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-static inline unsigned long long global_timer_ns() {
-    timespec t;
-    clock_gettime(CLOCK_MONOTONIC, &t);
-    return (unsigned long long)t.tv_sec * 1000000000ull + (unsigned long long)t.tv_nsec;
-}
-
 }  // namespace ofb
+
+#include "peer_on_host.h"  // peer_device.cuh's system-scope flag accesses
 
 #include "lk_march.cu"
 
