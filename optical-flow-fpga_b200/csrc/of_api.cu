@@ -228,6 +228,7 @@ struct PyrPlan {
 };
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+bool refine_chain_warp();  // below: OF_B200_REFINE_WARP=chain needs a second warped plane per level
 
 int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
     if (levels < 1 || levels > 16) return fail(OF_ERR_INVALID_ARGUMENT, "num_levels must be in 1..16");
@@ -262,7 +263,8 @@ int make_plan(int batch, int H, int W, int levels, PyrPlan& p) {
         p.bu_off[k] = off; off += bytes;
         p.bv_off[k] = off; off += bytes;
         p.warped_off[k] = off; off += bytes;
-        p.warped2_off[k] = off; off += bytes;
+        p.warped2_off[k] = p.warped_off[k];
+        if (refine_chain_warp()) { p.warped2_off[k] = off; off += bytes; }
         const int nb = lk_tile_blocks_per_pair(p.h[k], p.w[k]);
         if (nb > p.max_blocks) p.max_blocks = nb;
     }
