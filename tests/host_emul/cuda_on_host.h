@@ -114,6 +114,11 @@ static inline float __uint_as_float(unsigned i) {
     std::memcpy(&f, &i, 4);
     return f;
 }
+static inline unsigned __float_as_uint(float f) {
+    unsigned i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
 static inline int __float2int_rd(float f) { return (int)std::floor(f); }
 static inline int __double2int_rz(double d) { return (int)d; }
 static inline float __fmaf_rd(float a, float b, float c) {  // exact product and sum in float64, one rounding down
