@@ -560,6 +560,24 @@ def test_marching_kernel_uint8_ingest_and_fixed_point_flavours(emul_march, shape
             assert np.array_equal(u16[b], uo) and np.array_equal(v16[b], vo), (quirk, b)
 
 
+def test_uint8_flavour_with_the_sobel_stage_on_integer_fields(tmp_path_factory):
+    """-DOF_U8_INT_SOBEL=1 (a measured, switched-off option of lk_march.cu): q = prev + curr stays in packed 16-bit
+    fields and the Sobel sums are 32-bit additions on both fields at once.  Same bits as the reference, windows 5 and 7,
+    strips that end inside the frame, a height that is not a multiple of the chunk."""
+    lib = _build(tmp_path_factory, "emul_lk_march", defines=("-DOF_U8_INT_SOBEL=1",))
+    lib.emul_lk_march_u8.argtypes = [_vp] * 4 + [_i] * 4
+    for (h, w), window in (((33, 256), 5), ((20, 144), 7)):
+        rng = np.random.default_rng(h * w + window)
+        top = 256 if window == 5 else 128
+        p8 = rng.integers(0, top, (2, h, w)).astype(np.uint8)
+        c8 = rng.integers(0, top, (2, h, w)).astype(np.uint8)
+        u, v = np.full((2, h, w), np.nan, f32), np.full((2, h, w), np.nan, f32)
+        assert lib.emul_lk_march_u8(ptr(p8), ptr(c8), ptr(u), ptr(v), 2, h, w, window) == 0
+        for b in range(2):
+            uo, vo = orc.lucas_kanade_single_scale(p8[b].astype(f32), c8[b].astype(f32), window)
+            assert np.array_equal(bits(u[b]), bits(uo)) and np.array_equal(bits(v[b]), bits(vo)), (h, w, window, b)
+
+
 def _refine_once(lib, form, prev, curr, fu, fv, iteration=0, counter=None, state=None, rows=None, window=5,
                  warped=None, warped_next=None, warped_ready=0):
     b, h, w = prev.shape
