@@ -87,7 +87,11 @@ def hbm_peak():
 NCU_TRAFFIC = {
     # workload: (batch the capture was taken at, summary file)
     "single_1080p": (256, "r02_march_ncu_full_summary.json"),
+    "single_1080p_u8": (256, "r02_march_u8_ncu_full_summary.json"),
+    "fixed_1080p": (256, "r02_march_fx_ncu_full_summary.json"),
+    "single_1080p_exact": (64, "r02_exact_march_ncu_full_summary.json"),
 }
+_NCU_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def ncu_traffic_bytes(workload: str, batch: int):
@@ -101,8 +105,8 @@ def ncu_traffic_bytes(workload: str, batch: int):
         return None, None
     try:
         d = json.load(open(f))
-        rd = float(d["dram__bytes_read.sum"]["values"][0]) * 1e9
-        wr = float(d["dram__bytes_write.sum"]["values"][0]) * 1e9
+        rd = float(d["dram__bytes_read.sum"]["values"][0]) * _NCU_UNIT[d["dram__bytes_read.sum"]["unit"]]
+        wr = float(d["dram__bytes_write.sum"]["values"][0]) * _NCU_UNIT[d["dram__bytes_write.sum"]["unit"]]
         return rd + wr, f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/{cap[1]}"
     except Exception:
         return None, None

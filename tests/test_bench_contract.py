@@ -55,3 +55,17 @@ def test_pyramidal_byte_models_and_workload_table():
         cfg = bench.workload_config(name, wl)
         assert cfg["name"] == name and cfg["window"] == wl.get("window", 5) and f"{cfg['window']}x{cfg['window']} window" in cfg["workload"]
         assert "model" not in cfg
+
+
+def test_committed_ncu_captures_give_the_traffic_of_their_workloads():
+    """roofline.traffic comes from `ncu --set full` captures committed under profiles/: DRAM bytes of the dominant
+    kernel per launch.  For the single-launch workloads it must sit at the algorithmic bytes (no wasted re-reads)."""
+    import bench
+
+    for name, bpp in (("single_1080p", 16.0), ("single_1080p_u8", 10.0), ("fixed_1080p", 6.0), ("single_1080p_exact", 16.0)):
+        wl = bench.WORKLOADS[name]
+        traffic, src = bench.ncu_traffic_bytes(name, wl["batch"])
+        assert traffic is not None and "profiles/" in src, name
+        algorithmic = bpp * wl["batch"] * wl["H"] * wl["W"]
+        assert 0.97 < traffic / algorithmic < 1.03, (name, traffic / algorithmic)
+    assert bench.ncu_traffic_bytes("single_1080p", 128) == (None, None)  # a capture of another batch does not count
