@@ -216,9 +216,20 @@ void launch(dim3 grid, int threads, Kernel kernel) {
 }
 template <typename Kernel>
 void launch_dynamic(dim3 grid, dim3 block, size_t smem_bytes, Kernel kernel) {
+#ifdef OF_EMUL_EXACT_SMEM
+    // exactly the bytes the launch asked for, so that AddressSanitizer (tests/host_emul/asan_check.sh) sees any
+    // access past the kernel's dynamic shared memory
+    void* buf = nullptr;
+    if (posix_memalign(&buf, 128, smem_bytes ? smem_bytes : 128) != 0) abort();
+    dynamic_smem() = buf;
+    launch(grid, (int)block.x, kernel);
+    dynamic_smem() = nullptr;
+    free(buf);
+#else
     std::vector<char> buf(smem_bytes + 256);
     dynamic_smem() = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf.data()) + 127) & ~(uintptr_t)127);
     launch(grid, (int)block.x, kernel);
     dynamic_smem() = nullptr;
+#endif
 }
 }  // namespace cuda_on_host

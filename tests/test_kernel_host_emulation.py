@@ -16,6 +16,7 @@ a division); tests/test_gpu_parity.py covers that.
 """
 
 import ctypes as C
+import os
 import shutil
 import subprocess
 from pathlib import Path
@@ -41,8 +42,9 @@ def _build(tmp_path_factory, name, *more, defines=()):
         pytest.skip("needs g++ and the CUDA headers (vector types only; nothing CUDA is linked or run)")
     out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
     srcs = [str(ROOT / "tests" / "host_emul" / f"{n}.cpp") for n in (name,) + more]
+    extra = os.environ.get("OF_EMUL_EXTRA_FLAGS", "").split()  # tests/host_emul/asan_check.sh: AddressSanitizer
     cmd = [gxx, "-O1", "-ffp-contract=off", "-frounding-math", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w",
-           "-DOF_HOST_EMULATION", *defines, "-I", str(CSRC), "-I", str(CUDA_INC), *srcs, "-o", str(out)]
+           "-DOF_HOST_EMULATION", *defines, *extra, "-I", str(CSRC), "-I", str(CUDA_INC), *srcs, "-o", str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     return C.CDLL(str(out))
